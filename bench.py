@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — fake-quant fwd+bwd throughput (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # our sm_100a path
+    python bench.py --impl reference [...]                        # reference CPU path (oracle port)
+
+A "step" is one pass of the hot path over one batch of synthetic input: one
+fake-quant forward + one backward (incl. the deterministic finalize) over a
+[C, N/C] fp32 tensor.  Default workload = BASELINE.json configs[1] headline
+point: per-channel (C=512) N=2^28 elements, GDNSQ/STE estimator with fused
+Philox noise, 4 bits.  GB/s = 20 B/element (8 fwd + 12 bwd) x N / t.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+BYTES_FWD, BYTES_BWD = 8, 12          # algorithmic bytes / element (fp32)
+METRIC = "fake-quant fwd+bwd GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=28)
+    ap.add_argument("--channels", type=int, default=512, help="0 = per-tensor activation style")
+    ap.add_argument("--bits", type=int, default=4)
+    ap.add_argument("--method", default="STE", choices=["STE", "LSQ", "AEWGS", "EWGS"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also run the config-2 sweep -> gpurun_out/")
+    ap.add_argument("--cpu-log2n", type=int, default=24)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_name(a):
+    lay = f"per-channel [C={a.channels}, N/C]" if a.channels else "per-tensor"
+    return (f"configs[1] quantizer microbench: {lay} fp32 N=2^{a.log2n}, {a.method}"
+            f"{' (GDNSQ, fused Philox noise)' if a.method == 'STE' else ''}, {a.bits} bits, fwd+bwd")
+
+
+def make_inputs(a, device, log2n=None):
+    """x~N(0,1) seed 0, go~N(0,1) seed 1."""
+    n = 1 << (log2n if log2n is not None else a.log2n)
+    gx = torch.Generator(device=device).manual_seed(0)
+    gg = torch.Generator(device=device).manual_seed(1)
+    if a.channels:
+        shape = (a.channels, n // a.channels)
+    else:
+        shape = (n,)
+    x = torch.randn(shape, device=device, generator=gx)
+    go = torch.randn(shape, device=device, generator=gg)
+    if a.channels:
+        mn = x.amin(1, keepdim=True)
+        mx = x.amax(1, keepdim=True)
+        scale = (mx - mn) / (2 ** a.bits - 1)        # calibration formula, minmaxobserver.py:82
+        zp, lo, hi = mn, None, None
+    else:
+        b = torch.tensor([-2.0], device=device)
+        scale = torch.exp2(torch.tensor([2.0 - a.bits], device=device))
+        zp, lo, hi = b, b, b + 4.0 - scale
+    return x, go, scale, zp, lo, hi
+
+
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def time_region(fn, steps, sync_dist):
+    """K steps between barrier+synchronize on both sides, CUDA events on the launching stream."""
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if sync_dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if sync_dist:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if sync_dist:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+# ---------------------------------------------------------------------------
+def run_ours(a):
+    import mhaq_b200
+    from mhaq_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n = 1 << a.log2n
+    x, go, scale, zp, lo, hi = make_inputs(a, dev)
+    lo_ = -math.inf if lo is None else lo
+    hi_ = math.inf if hi is None else hi
+    scale_p = scale.clone().requires_grad_(True)
+    launches = {"n": 0}
+
+    def step():
+        xs = x.requires_grad_(True)
+        xs.grad = None
+        scale_p.grad = None
+        y = mhaq_b200.fake_quant(xs, scale_p, zp, lo_, hi_, method=a.method)
+        y.backward(go)
+        launches["n"] += 3 + (2 if a.method == "AEWGS" else 0)
+        return y, xs.grad, scale_p.grad
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    with ClockSampler(local) as cs:
+        ms = time_region(step, a.steps, use_dist)
+    clocks = cs.summary()
+    n_l = launches["n"]
+    per_step = ms / a.steps
+    gbs = world * (BYTES_FWD + BYTES_BWD) * n / (per_step * 1e-3) / 1e9
+
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        # ---- per-kernel roofline, measured live with CUDA events on the launch stream ----
+        L = ops._Launch(x.detach(), scale, zp, lo_, hi_)
+        xd = x.detach()
+
+        def fwd_only():
+            ops._forward_impl(xd, L, True, False, False)
+
+        def bwd_only():
+            ops._backward_impl(go, xd, L, ops._method_id(a.method), False, None, True, philox=(1, 2))
+
+        for f in (fwd_only, bwd_only):
+            for _ in range(3):
+                f()
+        k = max(a.steps, 10)
+        t_f = time_region(fwd_only, k, False) / k
+        t_b = time_region(bwd_only, k, False) / k
+        bwd_bytes = BYTES_BWD + (8 if a.method == "AEWGS" else 0)
+        ach_b = bwd_bytes * n / (t_b * 1e-3) / 1e9
+        ach_f = BYTES_FWD * n / (t_f * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("fq_bwd_kernel_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": "fq_bwd_kernel (+finalize)", "achieved": round(ach_b, 1),
+                    "peak": peak, "unit": "GB/s", "frac": round(ach_b / peak, 4), "traffic": traffic,
+                    "peak_source": peak_src, "frac_of_8TBps_nominal": round(ach_b / 8000.0, 4),
+                    "bytes_per_elem": bwd_bytes, "ms_per_launch": round(t_b, 4),
+                    "fwd_kernel": {"achieved": round(ach_f, 1), "frac": round(ach_f / peak, 4),
+                                   "bytes_per_elem": BYTES_FWD, "ms_per_launch": round(t_f, 4)}}
+        out = {"metric": METRIC, "value": round(gbs, 1), "unit": "GB/s", "n_gpus": world,
+               "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(per_step, 4),
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "impl": "ours",
+               "config": {"workload": workload_name(a), "elements_per_gpu": n,
+                          "layout": [a.channels, n // a.channels] if a.channels else [n],
+                          "method": a.method, "bits": a.bits, "bytes_per_element": 20,
+                          "l2": "inputs (1 GiB each) far exceed the 126 MB L2; no flush needed",
+                          "multi_gpu": "replicas only (independent tensors per GPU, no data-path collective)"},
+               "frac_of_hbm_peak": round(gbs / world / peak, 4),
+               "roofline": roofline, "clocks": clocks, "gpu_launches": n_l}
+
+    # ---- end to end through the public API with HOST buffers -------------------------
+    if not a.no_e2e:
+        hx = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+        hg = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+        hx.copy_(x.detach()); hg.copy_(go)
+        hy = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+        hgx = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+        hgs = torch.empty(scale.shape, dtype=torch.float32).pin_memory()
+        dx = torch.empty_like(x.detach()); dg = torch.empty_like(go)
+
+        def e2e_step():
+            dx.copy_(hx, non_blocking=True)
+            dg.copy_(hg, non_blocking=True)
+            xs = dx.requires_grad_(True)
+            xs.grad = None
+            scale_p.grad = None
+            y = mhaq_b200.fake_quant(xs, scale_p, zp, lo_, hi_, method=a.method)
+            y.backward(dg)
+            hy.copy_(y.detach(), non_blocking=True)
+            hgx.copy_(xs.grad, non_blocking=True)
+            hgs.copy_(scale_p.grad, non_blocking=True)
+
+        ke = max(3, min(a.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        ms_e = time_region(e2e_step, ke, use_dist) / ke
+        if rank == 0:
+            out["e2e"] = {"value": round(world * 20 * n / (ms_e * 1e-3) / 1e9, 2), "unit": "GB/s",
+                          "h2d_bytes_per_step": 2 * 4 * n, "d2h_bytes_per_step": 2 * 4 * n + 4 * scale.numel(),
+                          "ms_per_step": round(ms_e, 3), "steps": ke,
+                          "api": "mhaq_b200.fake_quant(...).backward() with pinned host x/go in, y/gx/g_scale out"}
+        del hx, hg, hy, hgx, dx, dg
+
+    if rank == 0:
+        if not a.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(a, steps=5, warmup=2)
+        if a.sweep:
+            sweep(a, dev)
+        print(json.dumps(out), flush=True)
+    if use_dist:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------
+def cpu_baseline(a, steps, warmup):
+    """The reference's CPU quantizer path (oracle port, same ATen op sequence) on the host cores."""
+    from oracle import fq_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    log2n = min(a.cpu_log2n, a.log2n)
+    n = 1 << log2n
+    x, go, scale, zp, lo, hi = make_inputs(a, "cpu", log2n)
+    lo_ = -math.inf if lo is None else lo
+    hi_ = math.inf if hi is None else hi
+    sp = scale.clone().requires_grad_(True)
+
+    def step():
+        xs = x.requires_grad_(True)
+        xs.grad = None
+        sp.grad = None
+        y = O.fake_quant(xs, sp, zp, lo_, hi_, method=a.method)
+        y.backward(go)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(20 * n / dt / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
+            "ms_per_step": round(dt * 1e3, 2),
+            "sample": f"same workload cut to N=2^{log2n} elements, {warmup} warm-up + {steps} timed steps, "
+                      f"torch {torch.__version__} CPU, {cores} threads"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, a.steps)
+    cb = cpu_baseline(a, steps=min(steps, 10), warmup=max(1, min(a.warmup, 3)))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = {"metric": METRIC, "value": cb["value"], "unit": "GB/s", "n_gpus": world, "steps": min(steps, 10),
+           "warmup": max(1, min(a.warmup, 3)), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+           "config": {"workload": workload_name(a), "note": "reference CPU path = oracle port of the "
+                      "reference's ATen op sequence (the Python reference cannot travel to the GPU box)"},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------
+def sweep(a, dev):
+    """BASELINE config 2: N in 2^20..2^30, layouts, methods, bits.  Writes gpurun_out/sweep.json."""
+    import mhaq_b200
+    from mhaq_b200 import ops
+    peak, _ = peaks()
+    rows = []
+    for log2n in (20, 22, 24, 26, 28, 30):
+        for ch in (0, 64, 512, 4096):
+            for method in ("STE", "LSQ", "AEWGS"):
+                if method == "AEWGS" and ch == 0:
+                    continue
+                for bits in ((4,) if log2n != 28 else (1, 2, 4, 8)):
+                    b = argparse.Namespace(**vars(a))
+                    b.log2n, b.channels, b.method, b.bits = log2n, ch, method, bits
+                    try:
+                        x, go, scale, zp, lo, hi = make_inputs(b, dev)
+                    except torch.OutOfMemoryError:
+                        continue
+                    n = 1 << log2n
+                    lo_ = -math.inf if lo is None else lo
+                    hi_ = math.inf if hi is None else hi
+                    L = ops._Launch(x, scale, zp, lo_, hi_)
+                    mid = ops._method_id(method)
+                    f = lambda: ops._forward_impl(x, L, True, False, False)
+                    g = lambda: ops._backward_impl(go, x, L, mid, False, None, True, philox=(1, 2))
+                    reps = 50 if log2n <= 24 else (20 if log2n <= 28 else 5)
+                    res = {}
+                    for nm, fn, by in (("fwd", f, 8), ("bwd", g, 12 + (8 if method == "AEWGS" else 0))):
+                        for _ in range(5):
+                            fn()
+                        # small tensors stay in L2 between iterations: flush with a 256 MB write
+                        flush = torch.empty(64 << 20, dtype=torch.float32, device=dev) if log2n <= 24 else None
+                        ts = []
+                        for _ in range(reps):
+                            if flush is not None:
+                                flush.zero_()
+                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                            ts.append(e0.elapsed_time(e1))
+                        ts.sort()
+                        med = ts[len(ts) // 2]
+                        res[nm] = {"ms_median": round(med, 4), "ms_best": round(ts[0], 4),
+                                   "GBps": round(by * n / med / 1e6, 1), "frac": round(by * n / med / 1e6 / peak, 4)}
+                    tot = res["fwd"]["ms_median"] + res["bwd"]["ms_median"]
+                    by = 20 + (8 if method == "AEWGS" else 0)
+                    rows.append({"log2n": log2n, "channels": ch, "method": method, "bits": bits, **res,
+                                 "fwd_bwd_GBps": round(by * n / tot / 1e6, 1),
+                                 "fwd_bwd_frac": round(by * n / tot / 1e6 / peak, 4)})
+                    print("sweep", json.dumps(rows[-1]), file=sys.stderr, flush=True)
+                    del x, go, L
+                    torch.cuda.empty_cache()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump({"peak_GBps": peak, "rows": rows}, open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w"), indent=1)
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                             "(use --impl reference for the CPU baseline)")
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+/*
+ * mhaq_fq.h — C ABI of the B200 (sm_100a) fake-quantization hot path.
+ *
+ * This is the drop-in boundary for MHAQ's QAT quantizer ops.  Every entry
+ * point replaces a piece of the reference's PyTorch implementation (paths are
+ * relative to the reference checkout):
+ *
+ *   mhaq_fq_fwd_f32            Quantizer.quantize + Quantizer.dequantize
+ *                              src/quantization/gdnsq/gdnsq.py:189-229
+ *                              (+ QNoise.forward, gdnsq.py:13-16)
+ *   mhaq_fq_bwd_f32            autograd of the above: QNSTE/QNLSQ/QNEWGS/QNAEWGS
+ *                              .backward (gdnsq.py:35-57, 63-84, 90-107, 113-147)
+ *                              fused with torch's clamp/sub/div/mul/add backward
+ *   mhaq_fq_bwd_finalize_f32   the broadcast "sum_to_size" reductions autograd
+ *                              performs for scale / zero_point / min_val / max_val
+ *   mhaq_fq_aewgs_stats_f32    reduce_to_shape(num/e2/me) of QNAEWGS.backward
+ *   + _finalize                gdnsq.py:118-124, 150-152 (the caller all-reduces
+ *                              the packed [3*n_ch] buffer once, gdnsq.py:126-129)
+ *   mhaq_fq_rowstat_f32        weight.amin((1,2,3)) / amax of NoisyConv2d.forward
+ *                              (layers/gdnsq_conv2d.py:80-84) and
+ *                              ModelHelper.get_model_values (utils/model_helper.py:24-25)
+ *   mhaq_fq_minmax_finalize    q.aminmax() of NoisyAct.forward (layers/gdnsq_act.py:51-54)
+ *                              and the eval-mode asserts (gdnsq.py:211-217)
+ *   mhaq_fq_noise_f32          torch.randint_like(input, 2).sub_(0.5)  (gdnsq.py:54)
+ *
+ * Conventions
+ *   - fp32 only, CUDA only, contiguous tensors only.  No CPU fallback exists.
+ *   - All pointers are DEVICE pointers unless stated otherwise.  The caller
+ *     owns every buffer, including workspaces; nothing here allocates.
+ *   - A tensor is viewed as [n_rows][n_inner]; row r belongs to quantization
+ *     channel (r % n_ch).  Per-tensor: n_rows=1, n_ch=1.  Conv weight
+ *     (O,I,kh,kw) per-channel: n_rows=O, n_inner=I*kh*kw, n_ch=O.
+ *   - Each of scale / zp / lo / hi is an array indexed [ch * stride] with
+ *     stride 0 (one broadcast value) or 1 (one value per channel).  lo / hi may
+ *     be NULL meaning -inf / +inf (the weight quantizer).
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     stateless and re-entrant.  Return value: 0 on success, otherwise the
+ *     cudaError_t of the failed launch / a negative MHAQ_FQ_E* argument error.
+ *     No exceptions cross this boundary.
+ */
+#ifndef MHAQ_FQ_H_
+#define MHAQ_FQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MHAQ_FQ_ABI_VERSION 1
+
+/* gradient estimators — numeric values follow the reference enum
+ * QNMethod (src/quantization/gdnsq/gdnsq_utils.py:9-13). */
+#define MHAQ_FQ_STE 0
+#define MHAQ_FQ_EWGS 1
+#define MHAQ_FQ_AEWGS 2
+#define MHAQ_FQ_LSQ 3
+
+/* argument errors */
+#define MHAQ_FQ_EINVAL (-1)
+#define MHAQ_FQ_ENULL (-2)
+
+/* doubles per task in the backward / stats workspace */
+#define MHAQ_FQ_NPART 8
+
+int mhaq_fq_abi_version(void);
+const char *mhaq_fq_build_info(void);
+
+/* Number of workspace "tasks" the kernels use for a [n_rows][n_inner] tensor.
+ * Workspace size in bytes = tasks * MHAQ_FQ_NPART * sizeof(double). */
+int64_t mhaq_fq_num_tasks(int64_t n_rows, int64_t n_inner);
+int64_t mhaq_fq_workspace_bytes(int64_t n_rows, int64_t n_inner);
+
+/* Forward: y = rint((clamp(x,lo,hi) - zp) / s) * s + zp, each step one IEEE
+ * fp32 rounding (no FMA contraction, true division, round-half-even).
+ *   y      : fake-quantized output, or NULL
+ *   codes  : integer-valued fp32 codes rint(v), or NULL
+ *   minmax_ws : NULL, or a workspace (mhaq_fq_workspace_bytes) that receives
+ *            per-task {min code, max code, non-finite count} for
+ *            mhaq_fq_minmax_finalize (eval mode). */
+int mhaq_fq_fwd_f32(const float *x, float *y, float *codes,
+                    const float *scale, const float *zp, const float *lo, const float *hi,
+                    int scale_stride, int zp_stride, int lo_stride, int hi_stride,
+                    int64_t n_rows, int64_t n_inner, int64_t n_ch,
+                    double *minmax_ws, void *stream);
+
+/* out[0]=min code, out[1]=max code, out[2]=number of non-finite codes, over
+ * the whole tensor. */
+int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_inner,
+                            float *out3, void *stream);
+
+/* Backward of the fake-quant op.
+ *   go      : gradient w.r.t. y (go_is_code_grad=0) or w.r.t. the codes
+ *             returned by quantize() (go_is_code_grad=1)
+ *   x       : the forward input (the only tensor saved for backward)
+ *   gx      : gradient w.r.t. x, or NULL
+ *   method  : MHAQ_FQ_STE / EWGS / AEWGS / LSQ
+ *   r       : explicit noise tensor in {-0.5,+0.5} (parity runs), or NULL to
+ *             draw it in-kernel from Philox4x32-10 keyed by (seed, offset);
+ *             if philox_dev != NULL the kernel reads seed=philox_dev[0] and
+ *             adds philox_dev[1] to offset (CUDA-graph friendly).
+ *   aewgs_stats : [3*n_ch] per-channel means {num, e2, me} (AEWGS only)
+ *   ws      : workspace, mhaq_fq_workspace_bytes(n_rows,n_inner) bytes;
+ *             consumed by mhaq_fq_bwd_finalize_f32. */
+int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx,
+                    const float *scale, const float *zp, const float *lo, const float *hi,
+                    int scale_stride, int zp_stride, int lo_stride, int hi_stride,
+                    int64_t n_rows, int64_t n_inner, int64_t n_ch,
+                    int method, int go_is_code_grad,
+                    const float *r, uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                    const float *aewgs_stats, double *ws, void *stream);
+
+/* Deterministic second stage: per-channel sums in a fixed order, fp64.
+ * Each output is [n_ch] floats (or NULL to skip):
+ *   g_scale = d/d scale,  g_zp = d/d zero_point,  g_lo = d/d min_val,
+ *   g_hi = d/d max_val. */
+int mhaq_fq_bwd_finalize_f32(const double *ws, int64_t n_rows, int64_t n_inner, int64_t n_ch,
+                             float *g_scale, float *g_zp, float *g_lo, float *g_hi,
+                             void *stream);
+
+/* AEWGS statistics: per-channel sums of sign(g)*e, e*e, e  (e = rint(v)-v). */
+int mhaq_fq_aewgs_stats_f32(const float *go, const float *x,
+                            const float *scale, const float *zp, const float *lo, const float *hi,
+                            int scale_stride, int zp_stride, int lo_stride, int hi_stride,
+                            int64_t n_rows, int64_t n_inner, int64_t n_ch,
+                            int go_is_code_grad, double *ws, void *stream);
+
+/* stats[0*n_ch+c]=mean num, stats[1*n_ch+c]=mean e2, stats[2*n_ch+c]=mean e. */
+int mhaq_fq_aewgs_stats_finalize_f32(const double *ws, int64_t n_rows, int64_t n_inner,
+                                     int64_t n_ch, float *stats, void *stream);
+
+/* Per-row min / max / number of elements equal to the row min / to the row max
+ * (what amin/amax backward needs for its even split among ties).
+ * Any output may be NULL.  One pass over x. */
+int mhaq_fq_rowstat_f32(const float *x, int64_t n_rows, int64_t n_inner,
+                        float *row_min, float *row_max, float *n_at_min, float *n_at_max,
+                        void *stream);
+
+/* out[i] = gx[i] + (x[i]==row_min ? g_min[row]/n_at_min[row] : 0)
+ *                + (x[i]==row_max ? g_max[row]/n_at_max[row] : 0)
+ * — amin / amax backward fused into one pass (g_min / g_max may be NULL). */
+int mhaq_fq_rowstat_bwd_f32(const float *gx, const float *x, int64_t n_rows, int64_t n_inner,
+                            const float *row_min, const float *n_at_min, const float *g_min,
+                            const float *row_max, const float *n_at_max, const float *g_max,
+                            float *out, void *stream);
+
+/* Materialise the in-kernel noise stream: r[i] in {-0.5,+0.5}, identical to what
+ * mhaq_fq_bwd_f32 draws for the same (seed, offset, philox_dev, shape). */
+int mhaq_fq_noise_f32(float *r, int64_t n_rows, int64_t n_inner,
+                      uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                      void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHAQ_FQ_H_ */

@@ -1,0 +1,79 @@
+"""ctypes binding of the C ABI declared in ``include/mhaq_fq.h``.
+
+The shared library ``mhaq_b200/csrc/libmhaq_fq.so`` is built in-tree by
+``__graft_entry__.build()`` (or ``make -C mhaq_b200/csrc``).  There is no CPU
+or PyTorch fallback: if the library is missing, importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_int, c_int64, c_uint64, c_void_p, c_char_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmhaq_fq.so")
+
+ABI_VERSION = 1
+NPART = 8  # MHAQ_FQ_NPART
+
+# name -> (restype, argtypes); mirrors include/mhaq_fq.h one to one
+_P = c_void_p
+_SIGNATURES = {
+    "mhaq_fq_abi_version": (c_int, []),
+    "mhaq_fq_build_info": (c_char_p, []),
+    "mhaq_fq_num_tasks": (c_int64, [c_int64, c_int64]),
+    "mhaq_fq_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "mhaq_fq_fwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
+                                c_int64, c_int64, c_int64, _P, _P]),
+    "mhaq_fq_minmax_finalize": (c_int, [_P, c_int64, c_int64, _P, _P]),
+    "mhaq_fq_bwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
+                                c_int64, c_int64, c_int64, c_int, c_int, _P, c_uint64, c_uint64,
+                                _P, _P, _P, _P]),
+    "mhaq_fq_bwd_finalize_f32": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "mhaq_fq_aewgs_stats_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int,
+                                        c_int64, c_int64, c_int64, c_int, _P, _P]),
+    "mhaq_fq_aewgs_stats_finalize_f32": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),
+    "mhaq_fq_rowstat_f32": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "mhaq_fq_rowstat_bwd_f32": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mhaq_fq_noise_f32": (c_int, [_P, c_int64, c_int64, c_uint64, c_uint64, _P, _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class MhaqLibraryError(ImportError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise MhaqLibraryError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library has not been built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C mhaq_b200/csrc`. There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as exc:  # pragma: no cover - build/header mismatch
+            raise MhaqLibraryError(f"{LIB_PATH} does not export {name}") from exc
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.mhaq_fq_abi_version()
+    if got != ABI_VERSION:
+        raise MhaqLibraryError(f"ABI mismatch: library {got}, binding {ABI_VERSION}")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str) -> None:
+    """Turn a C-ABI return code into a RuntimeError (no exceptions cross the ABI)."""
+    if rc == 0:
+        return
+    if rc < 0:
+        names = {-1: "MHAQ_FQ_EINVAL (bad shape/stride/method)", -2: "MHAQ_FQ_ENULL (null pointer)"}
+        raise RuntimeError(f"{what}: {names.get(rc, rc)}")
+    raise RuntimeError(f"{what}: CUDA error {rc}")

@@ -1,0 +1,241 @@
+// fq_common.cuh — shared device helpers for the sm_100a fake-quant kernels.
+//
+// Work decomposition (shared by every streaming kernel in this library)
+// ---------------------------------------------------------------------
+// A tensor is [n_rows][n_inner] fp32, row r quantized with channel r % n_ch.
+// Each row is cut into
+//     sub-tiles   of 4096 elements  (= 128 threads x 8 iterations x float4)
+//     super-tiles of 16384 elements (= 4 sub-tiles = 32 iterations)
+// Inside a super-tile, thread `tid` of the 128-thread CTA owns the float4 at
+// element offset  it*512 + tid*4  for it = 0..31.  Every warp-level access is
+// therefore 512 contiguous bytes (four full 128-byte lines).
+// A *task* is `spt` consecutive sub-tiles of one row; one CTA runs one task at
+// a time and, in the reducing kernels, flushes one partial record per task, so
+// the reduction tree is a pure function of the tensor shape (deterministic,
+// no atomics).  The noise stream is defined on (row, position-in-row): one
+// Philox4x32-10 block (128 bits) covers the 32 float4s a thread owns in a
+// super-tile, bit 4*it+k for element k of iteration it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace mhaq {
+
+constexpr int kThreads = 128;              // threads per CTA
+constexpr int kIterElems = kThreads * 4;   // 512 elements per CTA iteration
+constexpr int kSubIters = 8;               // iterations per sub-tile
+constexpr int kSubElems = kIterElems * kSubIters;  // 4096
+constexpr int kSuperSubs = 4;              // sub-tiles per super-tile
+constexpr int kSuperElems = kSubElems * kSuperSubs;  // 16384
+constexpr int kU = 4;                      // independent 128-bit loads in flight per stream
+constexpr int kNPart = 8;                  // doubles per task record (MHAQ_FQ_NPART)
+constexpr int kMaxSpt = 64;
+constexpr int64_t kTargetTasks = 4096;
+
+struct Geom {
+    int64_t n_rows, n_inner, n_ch;
+    int64_t subs_per_row;   // ceil(n_inner / 4096)
+    int64_t tasks_per_row;  // ceil(subs_per_row / spt)
+    int64_t n_tasks;        // n_rows * tasks_per_row
+    int spt;                // sub-tiles per task (1,2,4,...,64)
+};
+
+// Pure function of the shape: host and device, forward/backward/finalize all
+// agree on it, which is what makes the workspace layout part of the ABI.
+__host__ __device__ inline Geom make_geom(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
+    Geom g;
+    g.n_rows = n_rows;
+    g.n_inner = n_inner;
+    g.n_ch = n_ch < 1 ? 1 : n_ch;
+    g.subs_per_row = (n_inner + kSubElems - 1) / kSubElems;
+    int64_t total = n_rows * g.subs_per_row;
+    int spt = 1;
+    while (spt < kMaxSpt && (int64_t)spt * 2 <= g.subs_per_row && total / (spt * 2) >= kTargetTasks)
+        spt *= 2;
+    g.spt = spt;
+    g.tasks_per_row = (g.subs_per_row + spt - 1) / spt;
+    g.n_tasks = n_rows * g.tasks_per_row;
+    return g;
+}
+
+struct QParams {
+    const float *scale, *zp, *lo, *hi;
+    int ss, zs, ls, hs;
+};
+
+// Per-channel constants held in registers for the lifetime of a task.
+struct QConst {
+    float s, zp, lo, hi;
+};
+
+__device__ __forceinline__ QConst load_qconst(const QParams &p, int64_t ch) {
+    QConst q;
+    q.s = __ldg(p.scale + ch * p.ss);
+    q.zp = __ldg(p.zp + ch * p.zs);
+    q.lo = p.lo ? __ldg(p.lo + ch * p.ls) : -INFINITY;
+    q.hi = p.hi ? __ldg(p.hi + ch * p.hs) : INFINITY;
+    return q;
+}
+
+// ---- memory access ---------------------------------------------------------
+// Streaming 128-bit load: read-only path, no L1 allocation (each element is
+// touched exactly once per kernel).
+__device__ __forceinline__ float4 ld_stream4(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream4(float *p, const float4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// Load the 4 elements a thread owns at row position p (p % 4 == 0).
+// VEC: one 128-bit access (requires 16-byte aligned row bases and n_inner % 4 == 0).
+// !VEC: four predicated scalar accesses (ragged / unaligned rows).
+template <bool VEC>
+__device__ __forceinline__ float4 load4(const float *row, int64_t p, int64_t n_inner) {
+    if (VEC) {
+        return ld_stream4(row + p);
+    } else {
+        float4 v;
+        v.x = (p + 0 < n_inner) ? __ldg(row + p + 0) : 0.f;
+        v.y = (p + 1 < n_inner) ? __ldg(row + p + 1) : 0.f;
+        v.z = (p + 2 < n_inner) ? __ldg(row + p + 2) : 0.f;
+        v.w = (p + 3 < n_inner) ? __ldg(row + p + 3) : 0.f;
+        return v;
+    }
+}
+template <bool VEC>
+__device__ __forceinline__ void store4(float *row, int64_t p, int64_t n_inner, const float4 &v) {
+    if (VEC) {
+        st_stream4(row + p, v);
+    } else {
+        if (p + 0 < n_inner) row[p + 0] = v.x;
+        if (p + 1 < n_inner) row[p + 1] = v.y;
+        if (p + 2 < n_inner) row[p + 2] = v.z;
+        if (p + 3 < n_inner) row[p + 3] = v.w;
+    }
+}
+// number of valid elements (0..4) of the float4 at row position p
+template <bool VEC>
+__device__ __forceinline__ int valid4(int64_t p, int64_t n_inner) {
+    if (VEC) return p < n_inner ? 4 : 0;
+    int64_t r = n_inner - p;
+    return r <= 0 ? 0 : (r >= 4 ? 4 : (int)r);
+}
+
+// ---- arithmetic contract ---------------------------------------------------
+// Every step below is a separate IEEE-754 fp32 round-to-nearest operation —
+// exactly what the reference's chain of ATen kernels does
+// (gdnsq.py:197-208, 229).  The file is compiled with --fmad=false and these
+// wrappers use the _rn intrinsics so no FMA contraction can sneak in.
+__device__ __forceinline__ float f_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float f_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b); }
+
+// torch.clamp(x, lo, hi): NaN in x propagates; lo > hi yields hi.
+__device__ __forceinline__ float f_clamp(float x, float lo, float hi) {
+    float c = (x < lo) ? lo : x;
+    return (c > hi) ? hi : c;
+}
+
+// ---- Philox4x32-10 ---------------------------------------------------------
+struct PhiloxKey {
+    uint32_t k0, k1;   // seed
+    uint32_t o0, o1;   // offset (per-call stream id)
+};
+
+__host__ __device__ inline uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0;
+        uint64_t p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// 128 random bits for (row, super-tile T, thread tid).
+__device__ __forceinline__ uint4 noise_block(const PhiloxKey &key, int64_t row,
+                                             int64_t supers_per_row, int64_t T, int tid) {
+    uint64_t pos = ((uint64_t)row * (uint64_t)supers_per_row + (uint64_t)T) * kThreads + tid;
+    return philox4x32_10((uint32_t)pos, (uint32_t)(pos >> 32), key.o0, key.o1, key.k0, key.k1);
+}
+// the 4 bits of iteration `it` (0..31): bit k <-> element k of the float4
+__device__ __forceinline__ uint32_t noise_nibble(const uint4 &b, int it) {
+    uint32_t w = (it < 16) ? ((it < 8) ? b.x : b.y) : ((it < 24) ? b.z : b.w);
+    return (w >> ((it & 7) * 4)) & 0xFu;
+}
+
+__device__ __forceinline__ PhiloxKey make_key(uint64_t seed, uint64_t offset,
+                                              const uint64_t *philox_dev) {
+    if (philox_dev) {
+        seed = philox_dev[0];
+        offset += philox_dev[1];
+    }
+    PhiloxKey k;
+    k.k0 = (uint32_t)seed;
+    k.k1 = (uint32_t)(seed >> 32);
+    k.o0 = (uint32_t)offset;
+    k.o1 = (uint32_t)(offset >> 32);
+    return k;
+}
+
+// ---- reductions ------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Decompose a task id.  All threads of the CTA compute the same values.
+struct Task {
+    int64_t row, ch;
+    int64_t q0, q1;      // sub-tile range within the row
+    int64_t row_off;     // element offset of the row start
+};
+__device__ __forceinline__ Task make_task(const Geom &g, int64_t t) {
+    Task k;
+    int64_t j;
+    if (g.tasks_per_row == 1) {
+        k.row = t;
+        j = 0;
+    } else if (g.n_rows == 1) {
+        k.row = 0;
+        j = t;
+    } else {
+        k.row = t / g.tasks_per_row;
+        j = t - k.row * g.tasks_per_row;
+    }
+    k.ch = (g.n_ch == 1) ? 0 : (k.row % g.n_ch);
+    k.q0 = j * g.spt;
+    k.q1 = k.q0 + g.spt;
+    if (k.q1 > g.subs_per_row) k.q1 = g.subs_per_row;
+    k.row_off = k.row * g.n_inner;
+    return k;
+}
+
+}  // namespace mhaq

@@ -1,0 +1,790 @@
+// mhaq_fq.cu — sm_100a fake-quantization kernels + the C ABI of include/mhaq_fq.h.
+//
+// Replaces, per quantized tensor, the ~8 (forward) and ~19-27 (backward)
+// separate ATen elementwise/reduction launches of the reference
+// (src/quantization/gdnsq/gdnsq.py:189-229 and the QN*.backward functions)
+// with ONE forward kernel (8 B/element) and ONE backward kernel
+// (12 B/element) plus a tiny deterministic finalize.  HBM-bandwidth bound by
+// design: 128-bit coalesced streaming accesses, per-channel constants in
+// registers, fp32 per-thread partial sums -> warp shuffle -> fp64 across
+// warps / tasks, no atomics.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo
+#include "fq_common.cuh"
+#include "../../include/mhaq_fq.h"
+
+using namespace mhaq;
+
+namespace {
+
+// float32(3.0 ** -0.5): the GDNSQ scale-gradient factor (gdnsq.py:55).
+__device__ constexpr float kInvSqrt3 = 0.57735026918962584f;
+__device__ constexpr float kEwgsDelta = 0.01f;   // gdnsq.py:99
+__device__ constexpr float kAewgsEps = 1e-3f;    // gdnsq.py:131
+__device__ constexpr float kAewgsCap = 0.99f;    // 1 - gap, gdnsq.py:136-139
+
+enum { NOISE_PHILOX = 0, NOISE_EXPLICIT = 1, NOISE_NONE = 2 };
+
+// ===========================================================================
+// Forward
+// ===========================================================================
+struct FwdStat {
+    float cmin, cmax;
+    unsigned bad;
+};
+
+__device__ __forceinline__ float fwd_elem(float x, const QConst &q, float &code) {
+    float c = f_clamp(x, q.lo, q.hi);            // gdnsq.py:197
+    float u = f_sub(c, q.zp);                    // gdnsq.py:199
+    float v = f_div(u, q.s);                     // gdnsq.py:204
+    code = rintf(v);                             // v + (round(v) - v), gdnsq.py:15,208
+    return f_add(f_mul(code, q.s), q.zp);        // gdnsq.py:229 (two roundings)
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads)
+fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restrict__ codes,
+              QParams prm, Geom g, double *__restrict__ mm_ws) {
+    const int tid = threadIdx.x;
+    __shared__ float s_red[3][kThreads / 32];
+    for (int64_t t = blockIdx.x; t < g.n_tasks; t += gridDim.x) {
+        const Task k = make_task(g, t);
+        const QConst q = load_qconst(prm, k.ch);
+        const float *xr = x + k.row_off;
+        float *yr = y ? y + k.row_off : nullptr;
+        float *cr = codes ? codes + k.row_off : nullptr;
+        FwdStat st = {INFINITY, -INFINITY, 0u};
+        for (int64_t sub = k.q0; sub < k.q1; ++sub) {
+            const int64_t base = sub * kSubElems + tid * 4;
+            const bool full = (sub + 1) * kSubElems <= g.n_inner;
+#pragma unroll
+            for (int b = 0; b < kSubIters / kU; ++b) {
+                float4 xv[kU];
+                int nv[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int64_t p = base + (int64_t)(b * kU + u) * kIterElems;
+                    nv[u] = full ? 4 : valid4<VEC>(p, g.n_inner);
+                    xv[u] = nv[u] ? load4<VEC>(xr, p, g.n_inner) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (!nv[u]) continue;
+                    const int64_t p = base + (int64_t)(b * kU + u) * kIterElems;
+                    float4 cv, yv;
+                    yv.x = fwd_elem(xv[u].x, q, cv.x);
+                    yv.y = fwd_elem(xv[u].y, q, cv.y);
+                    yv.z = fwd_elem(xv[u].z, q, cv.z);
+                    yv.w = fwd_elem(xv[u].w, q, cv.w);
+                    if (yr) store4<VEC>(yr, p, g.n_inner, yv);
+                    if (cr) store4<VEC>(cr, p, g.n_inner, cv);
+                    if (mm_ws) {
+                        const float ce[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (e < nv[u]) {
+                                st.cmin = fminf(st.cmin, ce[e]);
+                                st.cmax = fmaxf(st.cmax, ce[e]);
+                                st.bad += !(fabsf(ce[e]) < INFINITY);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (mm_ws) {
+            float mn = warp_min(st.cmin), mx = warp_max(st.cmax);
+            float bd = warp_sum((float)st.bad);
+            if ((tid & 31) == 0) {
+                s_red[0][tid >> 5] = mn;
+                s_red[1][tid >> 5] = mx;
+                s_red[2][tid >> 5] = bd;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                float a = s_red[0][0], b = s_red[1][0], c = s_red[2][0];
+                for (int w = 1; w < kThreads / 32; ++w) {
+                    a = fminf(a, s_red[0][w]);
+                    b = fmaxf(b, s_red[1][w]);
+                    c += s_red[2][w];
+                }
+                double *rec = mm_ws + t * kNPart;
+                rec[0] = a;
+                rec[1] = b;
+                rec[2] = c;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fq_minmax_finalize_kernel(const double *__restrict__ ws, int64_t n_tasks, float *__restrict__ out3) {
+    __shared__ double s[3][256];
+    double mn = INFINITY, mx = -INFINITY, bad = 0.0;
+    for (int64_t t = threadIdx.x; t < n_tasks; t += 256) {
+        mn = fmin(mn, ws[t * kNPart + 0]);
+        mx = fmax(mx, ws[t * kNPart + 1]);
+        bad += ws[t * kNPart + 2];
+    }
+    s[0][threadIdx.x] = mn;
+    s[1][threadIdx.x] = mx;
+    s[2][threadIdx.x] = bad;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s[0][threadIdx.x] = fmin(s[0][threadIdx.x], s[0][threadIdx.x + o]);
+            s[1][threadIdx.x] = fmax(s[1][threadIdx.x], s[1][threadIdx.x + o]);
+            s[2][threadIdx.x] += s[2][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out3[0] = (float)s[0][0];
+        out3[1] = (float)s[1][0];
+        out3[2] = (float)s[2][0];
+    }
+}
+
+// ===========================================================================
+// Backward
+// ===========================================================================
+struct Acc {
+    float se;  // sum go*e (+ estimator correction)  -> d/d scale via dequant-mul and div
+    float sn;  // estimator's own scale gradient (GDNSQ noise term / LSQ)
+    float sz;  // sum (go - g_u)                      -> d/d zero_point
+    float sl;  // sum g_u [x < lo]                    -> d/d min_val
+    float sh;  // sum g_u [x > hi]                    -> d/d max_val
+};
+
+struct BwdConst {
+    float smul;      // s (grad w.r.t. y) or 1 (grad w.r.t. codes)
+    float rs;        // 1/s, only used inside tolerance-checked sums
+    float delta;     // AEWGS per-channel delta
+    bool codegrad;
+    bool lo_lt_hi, lo_gt_hi;
+};
+
+template <int METHOD, bool CLAMP, int NOISE>
+__device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t bit,
+                                          const QConst &q, const BwdConst &bc, Acc &acc) {
+    // ---- recompute the forward (gdnsq.py:197-208) ----
+    float c;
+    bool in, lo_m = false, hi_m = false;
+    if (CLAMP) {
+        const bool p_lt = x < q.lo, p_gt = x > q.hi;
+        const float c1 = p_lt ? q.lo : x;
+        c = (c1 > q.hi) ? q.hi : c1;
+        in = (x >= q.lo) && (x <= q.hi);                 // clamp_backward mask
+        lo_m = p_lt && bc.lo_lt_hi;                      // clamp_backward_min_max
+        hi_m = p_gt || (p_lt && bc.lo_gt_hi);
+    } else {
+        c = x;
+        in = (x == x);
+    }
+    const float u = f_sub(c, q.zp);
+    const float v = f_div(u, q.s);
+    const float code = rintf(v);
+    const float e = f_sub(code, v);                      // round(v) - v, exact
+    // ---- gradient w.r.t. codes, then the estimator (QN*.backward) ----
+    const float g = f_mul(go, bc.smul);                  // MulBackward of code*s
+    float gi = 0.f, gv;
+    if (METHOD == MHAQ_FQ_STE || METHOD == MHAQ_FQ_LSQ) {
+        gv = __fmaf_rn(g, 0.f, g);                       // g + g*0   (gdnsq.py:50,78)
+    } else if (METHOD == MHAQ_FQ_EWGS) {
+        gi = f_mul(f_mul(-fabsf(g), e), kEwgsDelta);     // gdnsq.py:100
+        gv = f_add(g, gi);
+    } else {                                             // AEWGS, gdnsq.py:118-141
+        const float sg = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);
+        const float nf = f_mul(sg, e);
+        float gs = f_mul(bc.delta, nf);
+        gs = (gs > kAewgsCap) ? kAewgsCap : gs;          // clamp_max(1-gap)
+        gi = f_mul(-g, gs);
+        gv = f_add(g, gi);
+    }
+    const float gu = f_div(gv, q.s);                     // DivBackward (self)
+    const float gx = in ? gu : 0.f;                      // ClampBackward
+    // ---- parameter-gradient partial sums ----
+    if (!bc.codegrad) {
+        acc.se = __fmaf_rn(go, e, acc.se);               // go*code - g*(v/s) = go*(code-v)
+        if (METHOD == MHAQ_FQ_EWGS || METHOD == MHAQ_FQ_AEWGS)
+            acc.se = __fmaf_rn(-gi, f_mul(v, bc.rs), acc.se);
+        acc.sz += f_sub(go, gu);                         // (+zp of dequant) - (sub zp)
+    } else {
+        acc.se = __fmaf_rn(-gv, f_mul(v, bc.rs), acc.se);
+        acc.sz -= gu;
+    }
+    if (METHOD == MHAQ_FQ_LSQ) {
+        acc.sn = __fmaf_rn(g, e, acc.sn);                // gdnsq.py:81-82
+    } else if (NOISE == NOISE_EXPLICIT) {
+        acc.sn += f_mul(f_mul(kInvSqrt3, g), rv);        // gdnsq.py:54-55
+    } else {
+        const float t = f_mul(kInvSqrt3, g);
+        const float ts = __uint_as_float(__float_as_uint(t) ^ ((bit ^ 1u) << 31));
+        acc.sn = __fmaf_rn(ts, 0.5f, acc.sn);            // r = bit - 0.5
+    }
+    if (CLAMP) {
+        acc.sl += lo_m ? gu : 0.f;
+        acc.sh += hi_m ? gu : 0.f;
+    }
+    return gx;
+}
+
+template <int METHOD, bool CLAMP, int NOISE, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *__restrict__ gx,
+              QParams prm, Geom g, int codegrad, const float *__restrict__ r, uint64_t seed,
+              uint64_t offset, const uint64_t *__restrict__ philox_dev,
+              const float *__restrict__ aewgs_stats, double *__restrict__ ws) {
+    const int tid = threadIdx.x;
+    __shared__ float s_red[5][kThreads / 32];
+    PhiloxKey key = {0, 0, 0, 0};
+    if (NOISE == NOISE_PHILOX) key = make_key(seed, offset, philox_dev);
+    const int64_t supers_per_row = (g.n_inner + kSuperElems - 1) / kSuperElems;
+
+    for (int64_t t = blockIdx.x; t < g.n_tasks; t += gridDim.x) {
+        const Task k = make_task(g, t);
+        const QConst q = load_qconst(prm, k.ch);
+        BwdConst bc;
+        bc.codegrad = codegrad != 0;
+        bc.smul = bc.codegrad ? 1.f : q.s;
+        bc.rs = f_div(1.f, q.s);
+        bc.lo_lt_hi = q.lo < q.hi;
+        bc.lo_gt_hi = q.lo > q.hi;
+        bc.delta = 0.f;
+        if (METHOD == MHAQ_FQ_AEWGS) {
+            const float num = __ldg(aewgs_stats + 0 * g.n_ch + k.ch);
+            const float e2 = __ldg(aewgs_stats + 1 * g.n_ch + k.ch);
+            const float me = __ldg(aewgs_stats + 2 * g.n_ch + k.ch);
+            float den = f_sub(e2, f_mul(me, me));            // gdnsq.py:132
+            den = (den < kAewgsEps) ? kAewgsEps : den;       // clamp_min(eps)
+            bc.delta = f_div(num, den);                      // gdnsq.py:134
+        }
+        const float *xr = x + k.row_off;
+        const float *gr = go + k.row_off;
+        const float *rr = (NOISE == NOISE_EXPLICIT) ? r + k.row_off : nullptr;
+        float *gxr = gx ? gx + k.row_off : nullptr;
+        Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f};
+        uint4 rnd = make_uint4(0, 0, 0, 0);
+        int64_t curT = -1;
+
+        for (int64_t sub = k.q0; sub < k.q1; ++sub) {
+            const int64_t base = sub * kSubElems + tid * 4;
+            const bool full = (sub + 1) * kSubElems <= g.n_inner;
+            const int it0 = (int)(sub & (kSuperSubs - 1)) * kSubIters;
+            if (NOISE == NOISE_PHILOX) {
+                const int64_t T = sub / kSuperSubs;
+                if (T != curT) {
+                    rnd = noise_block(key, k.row, supers_per_row, T, tid);
+                    curT = T;
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < kSubIters / kU; ++b) {
+                float4 xv[kU], gv[kU], rv4[kU];
+                int nv[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int64_t p = base + (int64_t)(b * kU + u) * kIterElems;
+                    nv[u] = full ? 4 : valid4<VEC>(p, g.n_inner);
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    xv[u] = nv[u] ? load4<VEC>(xr, p, g.n_inner) : z;
+                    gv[u] = nv[u] ? load4<VEC>(gr, p, g.n_inner) : z;
+                    rv4[u] = z;
+                    if (NOISE == NOISE_EXPLICIT && nv[u]) rv4[u] = load4<VEC>(rr, p, g.n_inner);
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (!nv[u]) continue;
+                    const int64_t p = base + (int64_t)(b * kU + u) * kIterElems;
+                    uint32_t nib = 0;
+                    if (NOISE == NOISE_PHILOX) nib = noise_nibble(rnd, it0 + b * kU + u);
+                    float4 o;
+                    o.x = bwd_elem<METHOD, CLAMP, NOISE>(xv[u].x, gv[u].x, rv4[u].x, (nib >> 0) & 1u, q, bc, acc);
+                    o.y = bwd_elem<METHOD, CLAMP, NOISE>(xv[u].y, gv[u].y, rv4[u].y, (nib >> 1) & 1u, q, bc, acc);
+                    o.z = bwd_elem<METHOD, CLAMP, NOISE>(xv[u].z, gv[u].z, rv4[u].z, (nib >> 2) & 1u, q, bc, acc);
+                    o.w = bwd_elem<METHOD, CLAMP, NOISE>(xv[u].w, gv[u].w, rv4[u].w, (nib >> 3) & 1u, q, bc, acc);
+                    if (gxr) store4<VEC>(gxr, p, g.n_inner, o);
+                }
+            }
+        }
+        // ---- flush one record per task: fp32 within a warp, fp64 across warps ----
+        float v0 = warp_sum(acc.se), v1 = warp_sum(acc.sn), v2 = warp_sum(acc.sz);
+        float v3 = CLAMP ? warp_sum(acc.sl) : 0.f, v4 = CLAMP ? warp_sum(acc.sh) : 0.f;
+        if ((tid & 31) == 0) {
+            const int w = tid >> 5;
+            s_red[0][w] = v0; s_red[1][w] = v1; s_red[2][w] = v2; s_red[3][w] = v3; s_red[4][w] = v4;
+        }
+        __syncthreads();
+        if (tid < 5) {
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) a += (double)s_red[tid][w];
+            ws[t * kNPart + tid] = a;
+        }
+        __syncthreads();
+    }
+}
+
+// One CTA per channel; fixed-order fp64 sums over the records of that channel.
+__global__ void __launch_bounds__(256)
+fq_bwd_finalize_kernel(const double *__restrict__ ws, Geom g, float *__restrict__ g_scale,
+                       float *__restrict__ g_zp, float *__restrict__ g_lo, float *__restrict__ g_hi) {
+    __shared__ double s[5][256];
+    const int64_t ch = blockIdx.x;
+    const int64_t rows_per_ch = g.n_rows / g.n_ch;
+    const int64_t recs = rows_per_ch * g.tasks_per_row;
+    double a[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = threadIdx.x; i < recs; i += 256) {
+        const int64_t rr = i / g.tasks_per_row;
+        const int64_t j = i - rr * g.tasks_per_row;
+        const int64_t t = (rr * g.n_ch + ch) * g.tasks_per_row + j;
+        const double *rec = ws + t * kNPart;
+#pragma unroll
+        for (int m = 0; m < 5; ++m) a[m] += rec[m];
+    }
+#pragma unroll
+    for (int m = 0; m < 5; ++m) s[m][threadIdx.x] = a[m];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+#pragma unroll
+            for (int m = 0; m < 5; ++m) s[m][threadIdx.x] += s[m][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (g_scale) g_scale[ch] = (float)(s[0][0] + s[1][0]);
+        if (g_zp) g_zp[ch] = (float)s[2][0];
+        if (g_lo) g_lo[ch] = (float)s[3][0];
+        if (g_hi) g_hi[ch] = (float)s[4][0];
+    }
+}
+
+// ===========================================================================
+// AEWGS statistics (gdnsq.py:118-124)
+// ===========================================================================
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads)
+fq_aewgs_stats_kernel(const float *__restrict__ go, const float *__restrict__ x, QParams prm, Geom g,
+                      int codegrad, double *__restrict__ ws) {
+    const int tid = threadIdx.x;
+    __shared__ float s_red[3][kThreads / 32];
+    for (int64_t t = blockIdx.x; t < g.n_tasks; t += gridDim.x) {
+        const Task k = make_task(g, t);
+        const QConst q = load_qconst(prm, k.ch);
+        const float smul = codegrad ? 1.f : q.s;
+        const float *xr = x + k.row_off;
+        const float *gr = go + k.row_off;
+        float a_num = 0.f, a_e2 = 0.f, a_e = 0.f;
+        for (int64_t sub = k.q0; sub < k.q1; ++sub) {
+            const int64_t base = sub * kSubElems + tid * 4;
+            const bool full = (sub + 1) * kSubElems <= g.n_inner;
+#pragma unroll
+            for (int b = 0; b < kSubIters / kU; ++b) {
+                float4 xv[kU], gv[kU];
+                int nv[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int64_t p = base + (int64_t)(b * kU + u) * kIterElems;
+                    nv[u] = full ? 4 : valid4<VEC>(p, g.n_inner);
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    xv[u] = nv[u] ? load4<VEC>(xr, p, g.n_inner) : z;
+                    gv[u] = nv[u] ? load4<VEC>(gr, p, g.n_inner) : z;
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const float xe[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                    const float ge[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (i < nv[u]) {
+                            const float c = f_clamp(xe[i], q.lo, q.hi);
+                            const float v = f_div(f_sub(c, q.zp), q.s);
+                            const float e = f_sub(rintf(v), v);
+                            const float gg = f_mul(ge[i], smul);
+                            const float sg = (gg > 0.f) ? 1.f : ((gg < 0.f) ? -1.f : 0.f);
+                            a_num += f_mul(sg, e);
+                            a_e2 += f_mul(e, e);
+                            a_e += e;
+                        }
+                    }
+                }
+            }
+        }
+        float v0 = warp_sum(a_num), v1 = warp_sum(a_e2), v2 = warp_sum(a_e);
+        if ((tid & 31) == 0) {
+            const int w = tid >> 5;
+            s_red[0][w] = v0; s_red[1][w] = v1; s_red[2][w] = v2;
+        }
+        __syncthreads();
+        if (tid < 3) {
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) a += (double)s_red[tid][w];
+            ws[t * kNPart + tid] = a;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fq_aewgs_stats_finalize_kernel(const double *__restrict__ ws, Geom g, float *__restrict__ stats) {
+    __shared__ double s[3][256];
+    const int64_t ch = blockIdx.x;
+    const int64_t rows_per_ch = g.n_rows / g.n_ch;
+    const int64_t recs = rows_per_ch * g.tasks_per_row;
+    double a[3] = {0, 0, 0};
+    for (int64_t i = threadIdx.x; i < recs; i += 256) {
+        const int64_t rr = i / g.tasks_per_row;
+        const int64_t j = i - rr * g.tasks_per_row;
+        const int64_t t = (rr * g.n_ch + ch) * g.tasks_per_row + j;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) a[m] += ws[t * kNPart + m];
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) s[m][threadIdx.x] = a[m];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+#pragma unroll
+            for (int m = 0; m < 3; ++m) s[m][threadIdx.x] += s[m][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double cnt = (double)rows_per_ch * (double)g.n_inner;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) stats[m * g.n_ch + ch] = (float)(s[m][0] / cnt);
+    }
+}
+
+// ===========================================================================
+// Noise materialisation (tests / parity): r = bit - 0.5
+// ===========================================================================
+__global__ void __launch_bounds__(kThreads)
+fq_noise_kernel(float *__restrict__ r, Geom g, uint64_t seed, uint64_t offset,
+                const uint64_t *__restrict__ philox_dev) {
+    const int tid = threadIdx.x;
+    const PhiloxKey key = make_key(seed, offset, philox_dev);
+    const int64_t supers_per_row = (g.n_inner + kSuperElems - 1) / kSuperElems;
+    for (int64_t t = blockIdx.x; t < g.n_tasks; t += gridDim.x) {
+        const Task k = make_task(g, t);
+        float *rr = r + k.row_off;
+        for (int64_t sub = k.q0; sub < k.q1; ++sub) {
+            const uint4 rnd = noise_block(key, k.row, supers_per_row, sub / kSuperSubs, tid);
+            const int it0 = (int)(sub & (kSuperSubs - 1)) * kSubIters;
+            for (int it = 0; it < kSubIters; ++it) {
+                const int64_t p = sub * kSubElems + (int64_t)it * kIterElems + tid * 4;
+                const uint32_t nib = noise_nibble(rnd, it0 + it);
+                for (int e = 0; e < 4; ++e)
+                    if (p + e < g.n_inner) rr[p + e] = ((nib >> e) & 1u) ? 0.5f : -0.5f;
+            }
+        }
+    }
+}
+
+// ===========================================================================
+// Row statistics (amin / amax with tie counts) and their backward
+// ===========================================================================
+struct RowStat {
+    float mn, mx, cmn, cmx;
+};
+__device__ __forceinline__ void rs_push(RowStat &a, float v) {
+    if (v < a.mn) { a.mn = v; a.cmn = 1.f; } else if (v == a.mn) { a.cmn += 1.f; }
+    if (v > a.mx) { a.mx = v; a.cmx = 1.f; } else if (v == a.mx) { a.cmx += 1.f; }
+}
+__device__ __forceinline__ void rs_merge(RowStat &a, const RowStat &b) {
+    if (b.mn < a.mn) { a.mn = b.mn; a.cmn = b.cmn; } else if (b.mn == a.mn) { a.cmn += b.cmn; }
+    if (b.mx > a.mx) { a.mx = b.mx; a.cmx = b.cmx; } else if (b.mx == a.mx) { a.cmx += b.cmx; }
+}
+
+// One CTA per row (rows are weight rows: short).  Deterministic: the merge is
+// associative and commutative on (value, count) pairs.
+__global__ void __launch_bounds__(kThreads)
+fq_rowstat_kernel(const float *__restrict__ x, int64_t n_rows, int64_t n_inner,
+                  float *__restrict__ row_min, float *__restrict__ row_max,
+                  float *__restrict__ n_at_min, float *__restrict__ n_at_max) {
+    __shared__ RowStat s[kThreads / 32];
+    const int tid = threadIdx.x;
+    for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const float *xr = x + row * n_inner;
+        RowStat a = {INFINITY, -INFINITY, 0.f, 0.f};
+        const bool vec = ((n_inner & 3) == 0) && ((reinterpret_cast<uintptr_t>(xr) & 15) == 0);
+        if (vec) {
+            for (int64_t p = tid * 4; p < n_inner; p += kIterElems) {
+                const float4 v = ld_stream4(xr + p);
+                rs_push(a, v.x); rs_push(a, v.y); rs_push(a, v.z); rs_push(a, v.w);
+            }
+        } else {
+            for (int64_t p = tid; p < n_inner; p += kThreads) rs_push(a, __ldg(xr + p));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            RowStat b;
+            b.mn = __shfl_xor_sync(0xffffffffu, a.mn, o);
+            b.mx = __shfl_xor_sync(0xffffffffu, a.mx, o);
+            b.cmn = __shfl_xor_sync(0xffffffffu, a.cmn, o);
+            b.cmx = __shfl_xor_sync(0xffffffffu, a.cmx, o);
+            rs_merge(a, b);
+        }
+        if ((tid & 31) == 0) s[tid >> 5] = a;
+        __syncthreads();
+        if (tid == 0) {
+            RowStat z = s[0];
+            for (int w = 1; w < kThreads / 32; ++w) rs_merge(z, s[w]);
+            if (row_min) row_min[row] = z.mn;
+            if (row_max) row_max[row] = z.mx;
+            if (n_at_min) n_at_min[row] = z.cmn;
+            if (n_at_max) n_at_max[row] = z.cmx;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+fq_rowstat_bwd_kernel(const float *__restrict__ gx, const float *__restrict__ x, int64_t n_rows,
+                      int64_t n_inner, const float *__restrict__ row_min,
+                      const float *__restrict__ n_at_min, const float *__restrict__ g_min,
+                      const float *__restrict__ row_max, const float *__restrict__ n_at_max,
+                      const float *__restrict__ g_max, float *__restrict__ out) {
+    const int tid = threadIdx.x;
+    for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const int64_t off = row * n_inner;
+        float mn = 0.f, mx = 0.f, dmn = 0.f, dmx = 0.f;
+        const bool has_mn = g_min != nullptr, has_mx = g_max != nullptr;
+        if (has_mn) { mn = row_min[row]; dmn = f_div(g_min[row], n_at_min[row]); }
+        if (has_mx) { mx = row_max[row]; dmx = f_div(g_max[row], n_at_max[row]); }
+        for (int64_t p = tid; p < n_inner; p += kThreads) {
+            const float xv = __ldg(x + off + p);
+            float o = gx ? __ldg(gx + off + p) : 0.f;
+            if (has_mn && xv == mn) o = f_add(o, dmn);
+            if (has_mx && xv == mx) o = f_add(o, dmx);
+            out[off + p] = o;
+        }
+    }
+}
+
+// ===========================================================================
+// Host-side launch helpers
+// ===========================================================================
+inline int check_common(const void *x, const float *scale, const float *zp, int64_t n_rows,
+                        int64_t n_inner, int64_t n_ch) {
+    if (!x || !scale || !zp) return MHAQ_FQ_ENULL;
+    if (n_rows < 0 || n_inner < 0 || n_ch < 1) return MHAQ_FQ_EINVAL;
+    if (n_rows > 0 && (n_rows % n_ch) != 0) return MHAQ_FQ_EINVAL;
+    return 0;
+}
+inline bool stride_ok(int s) { return s == 0 || s == 1; }
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline int grid_for(int64_t n_tasks) {
+    // Non-persistent: one CTA per task, hardware block scheduler balances the
+    // SMs.  (Tasks are >= 4096 elements so a 2^31-1 grid covers 8 Ti elements.)
+    const int64_t cap = 0x7fffffffLL;
+    return (int)(n_tasks < cap ? n_tasks : cap);
+}
+
+inline int last_error() {
+    cudaError_t e = cudaGetLastError();
+    return (int)e;
+}
+
+template <int METHOD, bool CLAMP, int NOISE>
+int launch_bwd(bool vec, int grid, cudaStream_t st, const float *go, const float *x, float *gx,
+               const QParams &prm, const Geom &g, int codegrad, const float *r, uint64_t seed,
+               uint64_t offset, const uint64_t *philox_dev, const float *stats, double *ws) {
+    if (vec)
+        fq_bwd_kernel<METHOD, CLAMP, NOISE, true><<<grid, kThreads, 0, st>>>(
+            go, x, gx, prm, g, codegrad, r, seed, offset, philox_dev, stats, ws);
+    else
+        fq_bwd_kernel<METHOD, CLAMP, NOISE, false><<<grid, kThreads, 0, st>>>(
+            go, x, gx, prm, g, codegrad, r, seed, offset, philox_dev, stats, ws);
+    return last_error();
+}
+
+template <int METHOD, bool CLAMP>
+int launch_bwd_noise(bool explicit_r, bool vec, int grid, cudaStream_t st, const float *go,
+                     const float *x, float *gx, const QParams &prm, const Geom &g, int codegrad,
+                     const float *r, uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                     const float *stats, double *ws) {
+    if (METHOD == MHAQ_FQ_LSQ)
+        return launch_bwd<METHOD, CLAMP, NOISE_NONE>(vec, grid, st, go, x, gx, prm, g, codegrad, r,
+                                                     seed, offset, philox_dev, stats, ws);
+    if (explicit_r)
+        return launch_bwd<METHOD, CLAMP, NOISE_EXPLICIT>(vec, grid, st, go, x, gx, prm, g, codegrad,
+                                                         r, seed, offset, philox_dev, stats, ws);
+    return launch_bwd<METHOD, CLAMP, NOISE_PHILOX>(vec, grid, st, go, x, gx, prm, g, codegrad, r,
+                                                   seed, offset, philox_dev, stats, ws);
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int mhaq_fq_abi_version(void) { return MHAQ_FQ_ABI_VERSION; }
+
+const char *mhaq_fq_build_info(void) {
+    return "mhaq_fq sm_100a fp32 fake-quant; cuda " __DATE__ " " __TIME__;
+}
+
+int64_t mhaq_fq_num_tasks(int64_t n_rows, int64_t n_inner) {
+    if (n_rows <= 0 || n_inner <= 0) return 0;
+    return make_geom(n_rows, n_inner, 1).n_tasks;
+}
+
+int64_t mhaq_fq_workspace_bytes(int64_t n_rows, int64_t n_inner) {
+    int64_t t = mhaq_fq_num_tasks(n_rows, n_inner);
+    if (t < 1) t = 1;
+    return t * kNPart * (int64_t)sizeof(double);
+}
+
+int mhaq_fq_fwd_f32(const float *x, float *y, float *codes, const float *scale, const float *zp,
+                    const float *lo, const float *hi, int scale_stride, int zp_stride,
+                    int lo_stride, int hi_stride, int64_t n_rows, int64_t n_inner, int64_t n_ch,
+                    double *minmax_ws, void *stream) {
+    int rc = check_common(x, scale, zp, n_rows, n_inner, n_ch);
+    if (rc) return rc;
+    if (!stride_ok(scale_stride) || !stride_ok(zp_stride) || !stride_ok(lo_stride) ||
+        !stride_ok(hi_stride))
+        return MHAQ_FQ_EINVAL;
+    if (n_rows == 0 || n_inner == 0) return 0;
+    const Geom g = make_geom(n_rows, n_inner, n_ch);
+    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride};
+    const bool vec = (n_inner % 4 == 0) && aligned16(x) && (!y || aligned16(y)) &&
+                     (!codes || aligned16(codes));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(g.n_tasks);
+    if (vec)
+        fq_fwd_kernel<true><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+    else
+        fq_fwd_kernel<false><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+    return last_error();
+}
+
+int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_inner, float *out3,
+                            void *stream) {
+    if (!minmax_ws || !out3) return MHAQ_FQ_ENULL;
+    const int64_t n_tasks = mhaq_fq_num_tasks(n_rows, n_inner);
+    if (n_tasks <= 0) return MHAQ_FQ_EINVAL;
+    fq_minmax_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(minmax_ws, n_tasks, out3);
+    return last_error();
+}
+
+int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx, const float *scale,
+                    const float *zp, const float *lo, const float *hi, int scale_stride,
+                    int zp_stride, int lo_stride, int hi_stride, int64_t n_rows, int64_t n_inner,
+                    int64_t n_ch, int method, int go_is_code_grad, const float *r, uint64_t seed,
+                    uint64_t offset, const uint64_t *philox_dev, const float *aewgs_stats,
+                    double *ws, void *stream) {
+    int rc = check_common(x, scale, zp, n_rows, n_inner, n_ch);
+    if (rc) return rc;
+    if (!go || !ws) return MHAQ_FQ_ENULL;
+    if (!stride_ok(scale_stride) || !stride_ok(zp_stride) || !stride_ok(lo_stride) ||
+        !stride_ok(hi_stride))
+        return MHAQ_FQ_EINVAL;
+    if (method < 0 || method > 3) return MHAQ_FQ_EINVAL;
+    if (method == MHAQ_FQ_AEWGS && !aewgs_stats) return MHAQ_FQ_ENULL;
+    if (n_rows == 0 || n_inner == 0) return 0;
+    const Geom g = make_geom(n_rows, n_inner, n_ch);
+    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride};
+    const bool vec = (n_inner % 4 == 0) && aligned16(x) && aligned16(go) &&
+                     (!gx || aligned16(gx)) && (!r || aligned16(r));
+    const bool clamp = (lo != nullptr) || (hi != nullptr);
+    const bool er = (r != nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(g.n_tasks);
+#define MHAQ_BWD(M)                                                                              \
+    (clamp ? launch_bwd_noise<M, true>(er, vec, grid, st, go, x, gx, prm, g, go_is_code_grad, r, \
+                                       seed, offset, philox_dev, aewgs_stats, ws)                \
+           : launch_bwd_noise<M, false>(er, vec, grid, st, go, x, gx, prm, g, go_is_code_grad,   \
+                                        r, seed, offset, philox_dev, aewgs_stats, ws))
+    switch (method) {
+        case MHAQ_FQ_STE: return MHAQ_BWD(MHAQ_FQ_STE);
+        case MHAQ_FQ_EWGS: return MHAQ_BWD(MHAQ_FQ_EWGS);
+        case MHAQ_FQ_AEWGS: return MHAQ_BWD(MHAQ_FQ_AEWGS);
+        default: return MHAQ_BWD(MHAQ_FQ_LSQ);
+    }
+#undef MHAQ_BWD
+}
+
+int mhaq_fq_bwd_finalize_f32(const double *ws, int64_t n_rows, int64_t n_inner, int64_t n_ch,
+                             float *g_scale, float *g_zp, float *g_lo, float *g_hi, void *stream) {
+    if (!ws) return MHAQ_FQ_ENULL;
+    if (n_rows <= 0 || n_inner <= 0 || n_ch < 1 || (n_rows % n_ch) != 0) return MHAQ_FQ_EINVAL;
+    const Geom g = make_geom(n_rows, n_inner, n_ch);
+    fq_bwd_finalize_kernel<<<(int)n_ch, 256, 0, (cudaStream_t)stream>>>(ws, g, g_scale, g_zp, g_lo,
+                                                                       g_hi);
+    return last_error();
+}
+
+int mhaq_fq_aewgs_stats_f32(const float *go, const float *x, const float *scale, const float *zp,
+                            const float *lo, const float *hi, int scale_stride, int zp_stride,
+                            int lo_stride, int hi_stride, int64_t n_rows, int64_t n_inner,
+                            int64_t n_ch, int go_is_code_grad, double *ws, void *stream) {
+    int rc = check_common(x, scale, zp, n_rows, n_inner, n_ch);
+    if (rc) return rc;
+    if (!go || !ws) return MHAQ_FQ_ENULL;
+    if (n_rows == 0 || n_inner == 0) return 0;
+    const Geom g = make_geom(n_rows, n_inner, n_ch);
+    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride};
+    const bool vec = (n_inner % 4 == 0) && aligned16(x) && aligned16(go);
+    const int grid = grid_for(g.n_tasks);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec)
+        fq_aewgs_stats_kernel<true><<<grid, kThreads, 0, st>>>(go, x, prm, g, go_is_code_grad, ws);
+    else
+        fq_aewgs_stats_kernel<false><<<grid, kThreads, 0, st>>>(go, x, prm, g, go_is_code_grad, ws);
+    return last_error();
+}
+
+int mhaq_fq_aewgs_stats_finalize_f32(const double *ws, int64_t n_rows, int64_t n_inner,
+                                     int64_t n_ch, float *stats, void *stream) {
+    if (!ws || !stats) return MHAQ_FQ_ENULL;
+    if (n_rows <= 0 || n_inner <= 0 || n_ch < 1 || (n_rows % n_ch) != 0) return MHAQ_FQ_EINVAL;
+    const Geom g = make_geom(n_rows, n_inner, n_ch);
+    fq_aewgs_stats_finalize_kernel<<<(int)n_ch, 256, 0, (cudaStream_t)stream>>>(ws, g, stats);
+    return last_error();
+}
+
+int mhaq_fq_rowstat_f32(const float *x, int64_t n_rows, int64_t n_inner, float *row_min,
+                        float *row_max, float *n_at_min, float *n_at_max, void *stream) {
+    if (!x) return MHAQ_FQ_ENULL;
+    if (n_rows < 0 || n_inner <= 0) return MHAQ_FQ_EINVAL;
+    if (n_rows == 0) return 0;
+    const int grid = grid_for(n_rows);
+    fq_rowstat_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, n_rows, n_inner, row_min,
+                                                                  row_max, n_at_min, n_at_max);
+    return last_error();
+}
+
+int mhaq_fq_rowstat_bwd_f32(const float *gx, const float *x, int64_t n_rows, int64_t n_inner,
+                            const float *row_min, const float *n_at_min, const float *g_min,
+                            const float *row_max, const float *n_at_max, const float *g_max,
+                            float *out, void *stream) {
+    if (!x || !out) return MHAQ_FQ_ENULL;
+    if ((g_min && (!row_min || !n_at_min)) || (g_max && (!row_max || !n_at_max)))
+        return MHAQ_FQ_ENULL;
+    if (n_rows < 0 || n_inner <= 0) return MHAQ_FQ_EINVAL;
+    if (n_rows == 0) return 0;
+    const int grid = grid_for(n_rows);
+    fq_rowstat_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+        gx, x, n_rows, n_inner, row_min, n_at_min, g_min, row_max, n_at_max, g_max, out);
+    return last_error();
+}
+
+int mhaq_fq_noise_f32(float *r, int64_t n_rows, int64_t n_inner, uint64_t seed, uint64_t offset,
+                      const uint64_t *philox_dev, void *stream) {
+    if (!r) return MHAQ_FQ_ENULL;
+    if (n_rows < 0 || n_inner < 0) return MHAQ_FQ_EINVAL;
+    if (n_rows == 0 || n_inner == 0) return 0;
+    const Geom g = make_geom(n_rows, n_inner, 1);
+    fq_noise_kernel<<<grid_for(g.n_tasks), kThreads, 0, (cudaStream_t)stream>>>(r, g, seed, offset,
+                                                                               philox_dev);
+    return last_error();
+}
+
+}  // extern "C"

@@ -1,0 +1,343 @@
+"""Autograd-level entry points of the B200 fake-quant path.
+
+``fake_quant`` is the fused replacement for the reference's
+``Q.dequantize(Q.quantize(x))`` (src/quantization/gdnsq/gdnsq.py:189-229);
+``quantize_codes`` is ``Q.quantize(x)`` alone.  Both run ONE sm_100a kernel in
+forward and ONE in backward (plus a tiny finalize), through the C ABI in
+``include/mhaq_fq.h``.  CUDA tensors only; there is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import lib, check
+
+METHOD_IDS = {"STE": 0, "EWGS": 1, "AEWGS": 2, "LSQ": 3}
+
+
+def _method_id(method) -> int:
+    """Accepts the reference's QNMethod enum (gdnsq_utils.py:9-13), its name or its value."""
+    if isinstance(method, int):
+        mid = method
+    elif isinstance(method, str):
+        mid = METHOD_IDS[method]
+    else:  # Enum
+        mid = int(method.value)
+    if mid not in (0, 1, 2, 3):
+        raise AttributeError(f"Unknown method {method}!")
+    return mid
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(x: torch.Tensor) -> None:
+    if not x.is_cuda:
+        raise RuntimeError(
+            "mhaq_b200 fake-quant kernels are CUDA (sm_100a) only; got a "
+            f"{x.device.type} tensor. There is no CPU fallback."
+        )
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"mhaq_b200 fake-quant is fp32 only, got {x.dtype}")
+
+
+class Geometry:
+    """[n_rows][n_inner] view of a tensor and the channel layout of its parameters."""
+
+    __slots__ = ("n_rows", "n_inner", "n_ch", "axis")
+
+    def __init__(self, n_rows: int, n_inner: int, n_ch: int, axis: Optional[int]):
+        self.n_rows, self.n_inner, self.n_ch, self.axis = n_rows, n_inner, n_ch, axis
+
+    def param_shape(self, x_shape: Sequence[int]) -> Tuple[int, ...]:
+        if self.axis is None:
+            return (1,)
+        return tuple(x_shape[d] if d == self.axis else 1 for d in range(len(x_shape)))
+
+
+def infer_geometry(x: torch.Tensor, params: Sequence[Optional[torch.Tensor]]) -> Geometry:
+    """Find the (single) channel axis the parameters broadcast along.
+
+    Per-tensor: every parameter has one element.  Per-channel: a parameter of
+    shape like (O,1,1,1) against x (O,I,kh,kw) — channel axis 0 — or (O,)
+    against a bias (O,).  (gdnsq_conv2d.py:53-56, 80-88.)
+    """
+    axis = None
+    for p in params:
+        if p is None or p.numel() == 1:
+            continue
+        shape = list(p.shape)
+        # right-align like broadcasting
+        shape = [1] * (x.dim() - len(shape)) + shape
+        if len(shape) != x.dim():
+            raise RuntimeError(f"parameter shape {tuple(p.shape)} does not broadcast to {tuple(x.shape)}")
+        nz = [d for d, s in enumerate(shape) if s != 1]
+        if len(nz) != 1 or shape[nz[0]] != x.shape[nz[0]]:
+            raise RuntimeError(
+                f"parameter shape {tuple(p.shape)}: only one broadcast (channel) axis is supported"
+            )
+        if axis is not None and axis != nz[0]:
+            raise RuntimeError("parameters disagree on the channel axis")
+        axis = nz[0]
+    n = x.numel()
+    if axis is None:
+        return Geometry(1, n, 1, None)
+    n_ch = x.shape[axis]
+    n_inner = 1
+    for d in range(axis + 1, x.dim()):
+        n_inner *= x.shape[d]
+    n_rows = n // n_inner if n_inner else 0
+    return Geometry(n_rows, n_inner, n_ch, axis)
+
+
+def _prep_param(p, x: torch.Tensor, name: str):
+    """-> (flat fp32 contiguous CUDA tensor or None, stride 0/1)."""
+    if p is None:
+        return None, 0
+    if not torch.is_tensor(p):
+        v = float(p)
+        if name == "lo" and v == -math.inf:
+            return None, 0
+        if name == "hi" and v == math.inf:
+            return None, 0
+        p = torch.full((1,), v, dtype=torch.float32, device=x.device)
+    if p.device != x.device:
+        p = p.to(x.device)
+    if p.dtype != torch.float32:
+        p = p.float()
+    flat = p.detach().contiguous().reshape(-1)
+    return flat, (0 if flat.numel() == 1 else 1)
+
+
+def _workspace(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
+    nbytes = lib.mhaq_fq_workspace_bytes(geo.n_rows, geo.n_inner)
+    return torch.empty(nbytes // 8, dtype=torch.float64, device=x.device)
+
+
+def _next_philox(device: torch.device) -> Tuple[int, int]:
+    """Draw a fresh (seed, offset) pair from torch's CUDA generator of `device`."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    gen = torch.cuda.default_generators[idx]
+    seed = gen.initial_seed()
+    off = gen.get_offset()
+    gen.set_offset(off + 4)
+    return seed & 0xFFFFFFFFFFFFFFFF, off // 4
+
+
+# Optional device-resident Philox state (uint64[2] = seed, step): makes the
+# backward CUDA-graph capturable because nothing host-side changes per step.
+_philox_dev = {}
+
+
+def set_device_philox_state(state: Optional[torch.Tensor]) -> None:
+    """state: int64 CUDA tensor [2] = (seed, step counter) read by the kernels."""
+    if state is None:
+        _philox_dev.clear()
+        return
+    assert state.is_cuda and state.dtype == torch.int64 and state.numel() == 2
+    _philox_dev[state.device.index] = state
+
+
+class _Launch:
+    """Flattened, validated launch description shared by forward and backward."""
+
+    def __init__(self, x, scale, zp, lo, hi):
+        _require_cuda(x)
+        self.geo = infer_geometry(x, [p for p in (scale, zp, lo, hi) if torch.is_tensor(p)])
+        self.scale, self.ss = _prep_param(scale, x, "scale")
+        self.zp, self.zs = _prep_param(zp, x, "zp")
+        self.lo, self.ls = _prep_param(lo, x, "lo")
+        self.hi, self.hs = _prep_param(hi, x, "hi")
+        if self.scale is None or self.zp is None:
+            raise RuntimeError("scale and zero_point are required")
+
+    def params(self):
+        return (_ptr(self.scale), _ptr(self.zp), _ptr(self.lo), _ptr(self.hi),
+                self.ss, self.zs, self.ls, self.hs)
+
+
+def _forward_impl(x, L: _Launch, want_y: bool, want_codes: bool, want_minmax: bool):
+    geo = L.geo
+    y = torch.empty_like(x) if want_y else None
+    codes = torch.empty_like(x) if want_codes else None
+    mm = None
+    ws = None
+    if x.numel() > 0:
+        if want_minmax:
+            ws = _workspace(x, geo)
+        check(lib.mhaq_fq_fwd_f32(_ptr(x), _ptr(y), _ptr(codes), *L.params(),
+                                  geo.n_rows, geo.n_inner, geo.n_ch, _ptr(ws), _stream()),
+              "mhaq_fq_fwd_f32")
+        if want_minmax:
+            mm = torch.empty(3, dtype=torch.float32, device=x.device)
+            check(lib.mhaq_fq_minmax_finalize(_ptr(ws), geo.n_rows, geo.n_inner, _ptr(mm), _stream()),
+                  "mhaq_fq_minmax_finalize")
+    return y, codes, mm
+
+
+def _reduce_to_param(g: torch.Tensor, param, geo: Geometry, x_shape):
+    """[n_ch] channel gradients -> gradient shaped like `param` (sum_to_size)."""
+    if not torch.is_tensor(param):
+        return None
+    if param.numel() == 1 and g.numel() > 1:
+        g = g.sum()
+    return g.reshape(param.shape).to(param.dtype)
+
+
+def aewgs_stats(go, x, L: _Launch, code_grad: bool) -> torch.Tensor:
+    """Packed per-channel means [3*n_ch] = (num, e2, me), all-reduced once (AVG) under DDP.
+
+    Reference: three reductions + three all_reduce calls (gdnsq.py:118-129)."""
+    geo = L.geo
+    ws = _workspace(x, geo)
+    stats = torch.empty(3 * geo.n_ch, dtype=torch.float32, device=x.device)
+    check(lib.mhaq_fq_aewgs_stats_f32(_ptr(go), _ptr(x), *L.params(), geo.n_rows, geo.n_inner,
+                                      geo.n_ch, int(code_grad), _ptr(ws), _stream()),
+          "mhaq_fq_aewgs_stats_f32")
+    check(lib.mhaq_fq_aewgs_stats_finalize_f32(_ptr(ws), geo.n_rows, geo.n_inner, geo.n_ch,
+                                               _ptr(stats), _stream()),
+          "mhaq_fq_aewgs_stats_finalize_f32")
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(stats, op=dist.ReduceOp.AVG)
+    return stats
+
+
+def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_gx: bool,
+                   philox=None):
+    geo = L.geo
+    go = go.contiguous()
+    gx = torch.empty_like(x) if need_gx else None
+    n_ch = geo.n_ch
+    out = torch.zeros(4, n_ch, dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return gx, out
+    if method == METHOD_IDS["AEWGS"] and geo.axis is None:
+        raise NotImplementedError(
+            "per-tensor AEWGS reduces its statistics over dim 0 only in the reference "
+            "(gdnsq.py:150-152 with scale.shape == (1,)); not supported by the fused path yet"
+        )
+    stats = aewgs_stats(go, x, L, code_grad) if method == METHOD_IDS["AEWGS"] else None
+    ws = _workspace(x, geo)
+    seed = offset = 0
+    pdev = None
+    if noise is not None:
+        noise = noise.contiguous()
+        if noise.shape != x.shape or noise.dtype != torch.float32 or not noise.is_cuda:
+            raise RuntimeError("explicit noise must be an fp32 CUDA tensor shaped like the input")
+    elif method != METHOD_IDS["LSQ"]:
+        if philox is not None:
+            seed, offset = philox
+        else:
+            pd = _philox_dev.get(x.device.index)
+            if pd is not None:
+                pdev = pd
+            else:
+                seed, offset = _next_philox(x.device)
+    check(lib.mhaq_fq_bwd_f32(_ptr(go), _ptr(x), _ptr(gx), *L.params(),
+                              geo.n_rows, geo.n_inner, geo.n_ch, method, int(code_grad),
+                              _ptr(noise), seed, offset, _ptr(pdev), _ptr(stats), _ptr(ws), _stream()),
+          "mhaq_fq_bwd_f32")
+    check(lib.mhaq_fq_bwd_finalize_f32(_ptr(ws), geo.n_rows, geo.n_inner, geo.n_ch,
+                                       _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]),
+                                       _stream()),
+          "mhaq_fq_bwd_finalize_f32")
+    return gx, out
+
+
+class _FakeQuantFn(torch.autograd.Function):
+    """y = dequantize(quantize(x)); saves only x and the O(channels) parameters."""
+
+    @staticmethod
+    def forward(ctx, x, scale, zp, lo, hi, method, noise, philox, code_only):
+        x = x.contiguous()
+        L = _Launch(x, scale, zp, lo, hi)
+        y, codes, _ = _forward_impl(x, L, want_y=not code_only, want_codes=code_only,
+                                    want_minmax=False)
+        ctx.save_for_backward(x, *(p for p in (scale, zp, lo, hi) if torch.is_tensor(p)))
+        ctx.meta = (tuple(torch.is_tensor(p) for p in (scale, zp, lo, hi)),
+                    tuple(None if torch.is_tensor(p) else p for p in (scale, zp, lo, hi)))
+        ctx.method, ctx.noise, ctx.philox, ctx.code_only = method, noise, philox, code_only
+        return codes if code_only else y
+
+    @staticmethod
+    def backward(ctx, go):
+        saved = list(ctx.saved_tensors)
+        x = saved.pop(0)
+        is_t, consts = ctx.meta
+        prm = [saved.pop(0) if t else c for t, c in zip(is_t, consts)]
+        scale, zp, lo, hi = prm
+        L = _Launch(x, scale, zp, lo, hi)
+        need = ctx.needs_input_grad
+        gx, out = _backward_impl(go, x, L, ctx.method, ctx.code_only, ctx.noise, need[0], ctx.philox)
+        geo = L.geo
+        grads = [gx if need[0] else None]
+        for i, p in enumerate(prm):
+            if is_t[i] and need[1 + i]:
+                grads.append(_reduce_to_param(out[i], p, geo, x.shape))
+            else:
+                grads.append(None)
+        return (*grads, None, None, None, None)
+
+
+def fake_quant(x, scale, zero_point, min_val=None, max_val=None, method="STE", noise=None,
+               philox=None):
+    """Fused fake-quantization with the reference's gradients.
+
+    Forward (bit-exact to gdnsq.py:197-208, 229):
+        y = rint((clamp(x, min_val, max_val) - zero_point) / scale) * scale + zero_point
+    Backward: gradients for x, scale, zero_point, min_val, max_val exactly as
+    autograd derives them for the reference graph with estimator ``method``
+    (QNSTE / QNEWGS / QNAEWGS / QNLSQ).  ``noise``: explicit {-0.5,+0.5} tensor
+    standing in for ``randint_like(v,2)-0.5`` (parity runs); default draws it
+    in-kernel from Philox keyed by torch's CUDA generator.
+    """
+    return _FakeQuantFn.apply(x, scale, zero_point, min_val, max_val, _method_id(method), noise,
+                              philox, False)
+
+
+def quantize_codes(x, scale, zero_point, min_val=None, max_val=None, method="STE", noise=None,
+                   philox=None):
+    """``Quantizer.quantize`` alone: integer-valued fp32 codes, differentiable."""
+    return _FakeQuantFn.apply(x, scale, zero_point, min_val, max_val, _method_id(method), noise,
+                              philox, True)
+
+
+def quantize_eval(x, scale, zero_point, min_val=None, max_val=None, want_y=True, want_codes=False):
+    """No-grad forward that also returns (min code, max code, #non-finite codes) as a
+    3-element CUDA tensor — the eval-mode extras of gdnsq.py:211-217 / gdnsq_act.py:51-54
+    in the same pass."""
+    x = x.detach().contiguous()
+    L = _Launch(x, scale, zero_point, min_val, max_val)
+    return _forward_impl(x, L, want_y, want_codes, True)
+
+
+def philox_noise(shape_like: torch.Tensor, scale_like=None, seed: int = 0, offset: int = 0):
+    """Materialise the kernels' noise stream r in {-0.5,+0.5} for `shape_like` (tests)."""
+    _require_cuda(shape_like)
+    geo = infer_geometry(shape_like, [scale_like] if torch.is_tensor(scale_like) else [])
+    r = torch.empty_like(shape_like, memory_format=torch.contiguous_format)
+    if r.numel():
+        check(lib.mhaq_fq_noise_f32(_ptr(r), geo.n_rows, geo.n_inner, seed, offset, None, _stream()),
+              "mhaq_fq_noise_f32")
+    return r
+
+
+def row_stats(x2d: torch.Tensor):
+    """(row_min, row_max, n_at_min, n_at_max) of a [rows, inner] view in one pass."""
+    _require_cuda(x2d)
+    x2d = x2d.contiguous()
+    rows, inner = x2d.shape
+    o = torch.empty(4, rows, dtype=torch.float32, device=x2d.device)
+    check(lib.mhaq_fq_rowstat_f32(_ptr(x2d), rows, inner, _ptr(o[0]), _ptr(o[1]), _ptr(o[2]),
+                                  _ptr(o[3]), _stream()), "mhaq_fq_rowstat_f32")
+    return o[0], o[1], o[2], o[3]

@@ -1,0 +1,74 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/mhaq_fq.h
+declares; argument validation works without a GPU (no kernel is launched)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mhaq_fq.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mhaq_fq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported():
+    from mhaq_b200 import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(raw, s), f"{s} declared in include/mhaq_fq.h but not exported"
+    assert set(syms) == set(_lib.EXPORTED_SYMBOLS), "ctypes binding out of sync with the header"
+
+
+def test_abi_version_and_info():
+    from mhaq_b200 import _lib
+    assert _lib.lib.mhaq_fq_abi_version() == 1
+    assert b"sm_100a" in _lib.lib.mhaq_fq_build_info()
+
+
+def test_geometry_is_a_pure_function_of_shape():
+    from mhaq_b200 import _lib
+    L = _lib.lib
+    assert L.mhaq_fq_num_tasks(1, 4096) == 1
+    assert L.mhaq_fq_num_tasks(1, 4097) == 2
+    assert L.mhaq_fq_num_tasks(512, 4608) == 1024
+    assert L.mhaq_fq_num_tasks(64, 576) == 64
+    assert L.mhaq_fq_num_tasks(0, 10) == 0
+    # large tensors are cut into >= 4096 tasks of up to 64 sub-tiles
+    assert L.mhaq_fq_num_tasks(1, 1 << 30) == 4096
+    assert L.mhaq_fq_workspace_bytes(1, 1 << 30) == 4096 * 8 * 8
+    n = 256 * 64 * 56 * 56
+    t = L.mhaq_fq_num_tasks(1, n)
+    assert 4096 <= t <= 8192 + 1
+
+
+def test_argument_errors_without_gpu():
+    from mhaq_b200 import _lib
+    L = _lib.lib
+    # null x / scale -> MHAQ_FQ_ENULL before anything touches CUDA
+    assert L.mhaq_fq_fwd_f32(None, None, None, None, None, None, None, 0, 0, 0, 0, 1, 8, 1, None, None) == -2
+    dummy = ctypes.c_void_p(16)
+    # bad stride
+    assert L.mhaq_fq_fwd_f32(dummy, dummy, None, dummy, dummy, None, None, 2, 0, 0, 0, 1, 8, 1, None, None) == -1
+    # rows not divisible by channels
+    assert L.mhaq_fq_fwd_f32(dummy, dummy, None, dummy, dummy, None, None, 1, 1, 0, 0, 5, 8, 2, None, None) == -1
+    # bad method
+    assert L.mhaq_fq_bwd_f32(dummy, dummy, dummy, dummy, dummy, None, None, 0, 0, 0, 0, 1, 8, 1, 9, 0,
+                             None, 0, 0, None, None, dummy, None) == -1
+    with pytest.raises(RuntimeError, match="EINVAL"):
+        _lib.check(-1, "x")
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through the oracle."""
+    pkg = os.path.join(ROOT, "mhaq_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

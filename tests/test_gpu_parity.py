@@ -1,0 +1,362 @@
+"""GPU parity: the sm_100a kernels (through the C ABI) vs the oracle.
+
+Bars (BASELINE.json north_star): fake-quant outputs and integer codes bit-exact;
+scale gradients within 1e-5 relative.  Input gradients are bit-exact too for
+STE / LSQ / EWGS; AEWGS input gradients depend on per-channel fp32 means and are
+held to 1e-5 relative.
+
+Scale-gradient rule.  d/ds is a sum of N signed terms that the reference
+accumulates in fp32 in three separately-rounded pieces which nearly cancel
+(SURVEY.md §7 "Hard parts"); its own result moves by more than 1e-5 relative
+with the summation order once codes are wide or N is large.  A value passes if
+    |ours - ref32| <= 1e-5 * |ref32|                       (the stated bar), or
+    |ours - exact| <= max(1e-5 * |exact|, |ref32 - exact|)  (never less accurate
+                                                            than the reference)
+where `exact` is the fp64 sum of the reference's own fp32 per-element terms.
+"""
+import math
+import zlib
+
+import pytest
+import torch
+
+from tests import helpers as H
+from oracle import fq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def fq():
+    import mhaq_b200
+    return mhaq_b200
+
+
+# ---------------------------------------------------------------------------
+# golden fixtures (outputs of the live reference)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", H.golden_names("act_"))
+def test_act_golden(fq, name):
+    c = H.load_golden(name)
+    r = H.run_act_case(c, fq.fake_quant, device="cuda")
+    H.assert_bit_exact(r["y"], c["y"], "y")
+    H.assert_bit_exact(r["gx"], c["gx"], "gx")
+    for k in ("g_log_act_s", "g_log_act_q", "g_act_b"):
+        if k in c:
+            H.assert_close_rel(r[k], c[k], REL, k, abs_floor=2e-6)
+    # two-call API (codes) and eval-mode extras in one pass
+    dev = "cuda"
+    s = torch.exp2(torch.tensor([float(c["log_act_s"])], device=dev))
+    q = torch.exp2(torch.tensor([float(c["log_act_q"])], device=dev))
+    b = torch.tensor([float(c["act_b"])], device=dev)
+    y, codes, mm = fq.quantize_eval(c["x"].to(dev), s, b, b, b + q - s, want_y=True, want_codes=True)
+    H.assert_bit_exact(codes, c["codes"], "codes")
+    H.assert_bit_exact(y, c["y"], "y(eval)")
+    mm = mm.cpu()
+    assert mm[2].item() == 0
+    bw = torch.log2(mm[1] - mm[0] + 1)
+    H.assert_bit_exact(bw, c["bw"], "bw")
+
+
+@pytest.mark.parametrize("name", H.golden_names("w_"))
+def test_weight_golden(fq, name):
+    c = H.load_golden(name)
+    r = H.run_weight_case(c, fq.fake_quant, device="cuda")
+    H.assert_bit_exact(r["wq"], c["wq"], "wq")
+    if c["method"] == "AEWGS":
+        H.assert_close_rel(r["g_weight"], c["g_weight"], REL, "g_weight", abs_floor=1e-6)
+    else:
+        # identical except for the amin-scattered zero-point term, which is pure
+        # fp32 rounding noise (sum(go) - sum(g_u)) in the reference
+        H.assert_close_rel(r["g_weight"], c["g_weight"], REL, "g_weight", abs_floor=2e-5)
+    H.assert_close_rel(r["g_log_wght_s"], c["g_log_wght_s"], REL, "g_log_wght_s", abs_floor=2e-6)
+    if "bq" in c:
+        H.assert_bit_exact(r["bq"], c["bq"], "bq")
+        H.assert_close_rel(r["g_bias"], c["g_bias"], REL, "g_bias", abs_floor=2e-5)
+
+
+def test_quantizer_codes_golden(fq):
+    c = H.load_golden("quantizer_codes_lsq", device="cuda")
+    x = c["x"].clone().requires_grad_(True)
+    scale = c["scale"].clone().requires_grad_(True)
+    zp = c["zp"].clone().requires_grad_(True)
+    codes = fq.quantize_codes(x, scale, zp, -math.inf, math.inf, method="LSQ")
+    codes.backward(c["gcodes"])
+    H.assert_bit_exact(codes, c["codes"], "codes")
+    H.assert_bit_exact(x.grad, c["gx"], "gx")
+    H.assert_close_rel(scale.grad, c["g_scale"], REL, "g_scale", abs_floor=2e-6)
+    H.assert_close_rel(zp.grad, c["g_zp"], REL, "g_zp", abs_floor=2e-6)
+
+
+# ---------------------------------------------------------------------------
+# seeded random cases vs the oracle, raw-parameter level
+# ---------------------------------------------------------------------------
+def _leafs(shape_x, per_channel, bits, clip, seed, device):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(shape_x, generator=g)
+    go = torch.randn(shape_x, generator=g)
+    if per_channel:
+        C = shape_x[0]
+        pshape = (C,) + (1,) * (len(shape_x) - 1)
+        flat = x.reshape(C, -1)
+        mn, mx = flat.amin(1).reshape(pshape), flat.amax(1).reshape(pshape)
+    else:
+        pshape = (1,)
+        mn, mx = x.min().reshape(1), x.max().reshape(1)
+    if clip:
+        lo = torch.full(pshape, -2.0) + 0.1 * torch.rand(pshape, generator=g)
+        q = 4.0
+        scale = torch.full(pshape, q / 2 ** bits) * (1 + 0.05 * torch.rand(pshape, generator=g))
+        hi = lo + q - scale
+        zp = lo.clone()
+    else:
+        lo = hi = None
+        scale = (mx - mn) / (2 ** bits - 1)
+        zp = mn.clone()
+    r = torch.randint(0, 2, shape_x, generator=g).float() - 0.5
+    mk = lambda t: None if t is None else t.to(device).clone().requires_grad_(True)
+    return x, go, r, scale, zp, lo, hi, mk
+
+
+def _run(fn, x, go, r, scale, zp, lo, hi, mk, method, device, expand=False):
+    xs = x.to(device).clone().requires_grad_(True)
+    P = [scale, zp, lo, hi]
+    if expand:  # per-element parameter gradients: fp32 terms, summed in fp64 below
+        P = [None if p is None else p.expand(x.shape).contiguous() for p in P]
+    s_, z_, l_, h_ = [mk(p) for p in P]
+    y = fn(xs, s_, z_, -math.inf if l_ is None else l_, math.inf if h_ is None else h_,
+           method=method, noise=None if method == "LSQ" else r.to(device))
+    y.backward(go.to(device))
+    grads = [None if p is None else p.grad for p in (s_, z_, l_, h_)]
+    return y.detach(), xs.grad, grads
+
+
+def _exact(grads_full, like):
+    out = []
+    for gfull, p in zip(grads_full, like):
+        if gfull is None:
+            out.append(None)
+            continue
+        g64 = gfull.double().cpu()
+        if p.numel() == 1:
+            out.append(g64.sum().reshape(p.shape))
+        else:
+            out.append(g64.reshape(p.shape[0], -1).sum(1).reshape(p.shape))
+    return out
+
+
+def _check_param_grad(ours, ref32, exact, what, abs_floor):
+    ours, ref32 = ours.detach().cpu().double().reshape(-1), ref32.detach().cpu().double().reshape(-1)
+    exact = exact.reshape(-1)
+    ok1 = (ours - ref32).abs() <= REL * ref32.abs() + abs_floor
+    ok2 = (ours - exact).abs() <= torch.maximum(REL * exact.abs(), (ref32 - exact).abs()) + abs_floor
+    ok = ok1 | ok2
+    if not bool(ok.all()):
+        i = int((~ok).nonzero()[0])
+        raise AssertionError(
+            f"{what}[{i}]: ours {ours[i].item():.9g} ref32 {ref32[i].item():.9g} exact "
+            f"{exact[i].item():.9g} (ours-ref32 rel {abs(ours[i]-ref32[i]).item()/max(abs(ref32[i]).item(),1e-30):.2e}, "
+            f"ref32-exact rel {abs(ref32[i]-exact[i]).item()/max(abs(exact[i]).item(),1e-30):.2e})")
+
+
+CASES = [
+    # shape, per_channel, bits, clip, method
+    ((2, 3, 20, 17), False, 4, True, "STE"),          # ragged per-tensor, one task
+    ((4, 16, 32, 32), False, 4, True, "STE"),         # 65536 = 16 sub-tiles
+    ((8, 16, 56, 56), False, 2, True, "STE"),         # 401408: several tasks + ragged tail
+    ((3, 5, 7, 11), False, 8, True, "STE"),           # odd sizes -> scalar path
+    ((64, 64, 3, 3), True, 4, False, "STE"),          # weight rows of 576
+    ((64, 64, 3, 3), True, 3, False, "LSQ"),
+    ((64, 64, 3, 3), True, 2, False, "AEWGS"),
+    ((64, 64, 3, 3), True, 2, False, "EWGS"),
+    ((32, 50, 3, 3), True, 2, False, "LSQ"),          # rows of 450 (RFDN): not a multiple of 4
+    ((32, 50, 3, 3), True, 1, False, "AEWGS"),
+    ((16, 512, 3, 3), True, 4, False, "STE"),         # rows of 4608: two sub-tiles per row
+    ((8, 40000), True, 5, True, "STE"),               # long rows: several tasks per row, clipped
+    ((1, 70000), False, 6, False, "LSQ"),             # per-tensor, no clamp
+    ((512,), False, 4, False, "STE"),
+]
+
+
+@pytest.mark.parametrize("shape,per_channel,bits,clip,method", CASES)
+def test_random_vs_oracle(fq, shape, per_channel, bits, clip, method):
+    seed = zlib.crc32(repr((shape, per_channel, bits, clip, method)).encode()) % 10000
+    x, go, r, scale, zp, lo, hi, mk = _leafs(shape, per_channel, bits, clip, seed, "cpu")
+    mk_cpu = lambda t: None if t is None else t.clone().requires_grad_(True)
+    mk_gpu = lambda t: None if t is None else t.to("cuda").clone().requires_grad_(True)
+    y_o, gx_o, g_o = _run(O.fake_quant, x, go, r, scale, zp, lo, hi, mk_cpu, method, "cpu")
+    _, _, g_full = _run(O.fake_quant, x, go, r, scale, zp, lo, hi, mk_cpu, method, "cpu", expand=True)
+    g_e = _exact(g_full, [scale, zp, lo, hi])
+    if method == "AEWGS":   # expanding the scale changes reduce_to_shape's dims: no exact form
+        g_e = [None if t is None else t.detach().double().cpu() for t in g_o]
+    y_g, gx_g, g_g = _run(fq.fake_quant, x, go, r, scale, zp, lo, hi, mk_gpu, method, "cuda")
+    H.assert_bit_exact(y_g, y_o, "y")
+    if method == "AEWGS":
+        H.assert_close_rel(gx_g, gx_o, REL, "gx", abs_floor=1e-7)
+    else:
+        H.assert_bit_exact(gx_g, gx_o, "gx")
+    n = x.numel() if not per_channel else x.numel() // shape[0]
+    floor = 2e-7 * math.sqrt(n) * 4      # fp32 rounding noise of an N-term sum of O(1) terms
+    for nm, a, b, e in zip(("g_scale", "g_zp", "g_lo", "g_hi"), g_g, g_o, g_e):
+        if b is None:
+            continue
+        _check_param_grad(a, b, e, nm, floor if nm != "g_scale" else floor * 0.25)
+
+
+@pytest.mark.parametrize("bits", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_bits_sweep_forward_bit_exact(fq, bits):
+    """BASELINE config 2 parameterisation: act_b=-2, log_act_q=2, log_act_s=2-bits."""
+    torch.manual_seed(bits)
+    x = torch.randn(1 << 20)
+    s = torch.exp2(torch.tensor([2.0 - bits]))
+    b = torch.tensor([-2.0])
+    hi = b + 4.0 - s
+    y_o = O.fake_quant(x, s, b, b, hi)
+    c_o = O.quantize(x, s, b, b, hi)
+    y_g, c_g, mm = fq.quantize_eval(x.cuda(), s.cuda(), b.cuda(), b.cuda(), hi.cuda(),
+                                    want_y=True, want_codes=True)
+    H.assert_bit_exact(y_g, y_o, "y")
+    H.assert_bit_exact(c_g, c_o, "codes")
+    assert mm[0].item() == c_o.min().item() and mm[1].item() == c_o.max().item()
+    assert c_o.max().item() <= 2 ** bits - 1
+
+
+def test_special_values(fq):
+    """NaN / inf / signed zero / exact ties / values on the clip bounds."""
+    s = torch.tensor([0.25])
+    b = torch.tensor([-1.0])
+    hi = torch.tensor([2.0])
+    vals = [float("nan"), float("inf"), -float("inf"), 0.0, -0.0, -1.0, 2.0, 2.0000002, -1.0000001,
+            -1.0 + 0.125, -1.0 + 0.375, -1.0 + 0.625, 1e-30, -1e30, 1.9999999]
+    x = torch.tensor(vals * 40)[:512].clone()
+    go = torch.ones_like(x)
+    for lo_, hi_ in ((b, hi), (None, None)):
+        xo = x.clone().requires_grad_(True)
+        y_o = O.fake_quant(xo, s, b, -math.inf if lo_ is None else lo_, math.inf if hi_ is None else hi_,
+                           method="LSQ")
+        y_o.backward(go)
+        xg = x.cuda().requires_grad_(True)
+        y_g = fq.fake_quant(xg, s.cuda(), b.cuda(), -math.inf if lo_ is None else lo_.cuda(),
+                            math.inf if hi_ is None else hi_.cuda(), method="LSQ")
+        y_g.backward(go.cuda())
+        H.assert_bit_exact(y_g, y_o, "y")
+        H.assert_bit_exact(xg.grad, xo.grad, "gx")
+
+
+def test_empty_and_tiny(fq):
+    s = torch.tensor([0.5], device="cuda", requires_grad=True)
+    z = torch.tensor([0.0], device="cuda")
+    x = torch.empty(0, 4, device="cuda", requires_grad=True)
+    y = fq.fake_quant(x, s, z)
+    assert y.shape == (0, 4)
+    y.sum().backward()
+    assert s.grad is not None and s.grad.item() == 0.0
+    x1 = torch.tensor([0.74], device="cuda", requires_grad=True)
+    y1 = fq.fake_quant(x1, s, z, method="LSQ")
+    assert y1.item() == 0.5
+    y1.backward(torch.ones_like(y1))
+    assert x1.grad.item() == 1.0
+
+
+def test_cpu_tensor_is_an_error(fq):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fq.fake_quant(torch.randn(8), torch.tensor([0.5]), torch.tensor([0.0]))
+
+
+# ---------------------------------------------------------------------------
+# in-kernel Philox noise
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,inner", [(1, 100000), (3, 16384 + 520), (5, 450), (2, 4096)])
+def test_philox_stream_matches_numpy(fq, rows, inner):
+    like = torch.empty(rows, inner, device="cuda")
+    sc = torch.empty(rows, 1, device="cuda") if rows > 1 else None
+    r = fq.philox_noise(like, sc, seed=0x1234567890ABCDEF, offset=77).cpu().numpy()
+    ref = O.philox_noise(rows, inner, 0x1234567890ABCDEF, 77)
+    assert (r == ref).all()
+    assert abs(float(r.mean())) < 0.02
+
+
+@pytest.mark.parametrize("shape,per_channel,clip", [((8, 16, 56, 56), False, True),
+                                                     ((64, 64, 3, 3), True, False)])
+def test_fused_noise_equals_explicit_noise(fq, shape, per_channel, clip):
+    """Drawing r in-kernel must give the SAME gradients as feeding the materialised r."""
+    x, go, _, scale, zp, lo, hi, _ = _leafs(shape, per_channel, 4, clip, 5, "cuda")
+    mk = lambda t: None if t is None else t.cuda().clone().requires_grad_(True)
+    seed, off = 99, 1234
+    r = fq.philox_noise(x.cuda(), scale.cuda() if per_channel else None, seed=seed, offset=off)
+
+    def run(noise, philox):
+        xs = x.cuda().requires_grad_(True)
+        s_, z_, l_, h_ = mk(scale), mk(zp), mk(lo), mk(hi)
+        y = fq.fake_quant(xs, s_, z_, -math.inf if l_ is None else l_, math.inf if h_ is None else h_,
+                          method="STE", noise=noise, philox=philox)
+        y.backward(go.cuda())
+        return xs.grad, s_.grad
+    gx_a, gs_a = run(r, None)
+    gx_b, gs_b = run(None, (seed, off))
+    assert torch.equal(gx_a, gx_b)
+    assert torch.equal(gs_a, gs_b), (gs_a - gs_b).abs().max()
+
+
+def test_deterministic(fq):
+    x, go, r, scale, zp, lo, hi, _ = _leafs((8, 16, 56, 56), False, 4, True, 11, "cuda")
+    mk = lambda t: t.cuda().clone().requires_grad_(True)
+    outs = []
+    for _ in range(3):
+        xs = x.cuda().requires_grad_(True)
+        s_, z_, l_, h_ = mk(scale), mk(zp), mk(lo), mk(hi)
+        y = fq.fake_quant(xs, s_, z_, l_, h_, method="STE", philox=(1, 2))
+        y.backward(go.cuda())
+        outs.append((y.detach(), xs.grad, s_.grad, z_.grad, l_.grad, h_.grad))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------
+# full-size checks (BASELINE config 2): the oracle's ATen chain runs on the GPU
+# itself as the checker; plus size-independent properties
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("log2n,bits", [(26, 4), (28, 8)])
+def test_full_size_vs_oracle_on_device(fq, log2n, bits):
+    n = 1 << log2n
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(n, device="cuda", generator=g)
+    g1 = torch.Generator(device="cuda").manual_seed(1)
+    go = torch.randn(n, device="cuda", generator=g1)
+    b = torch.tensor([-2.0], device="cuda")
+    s = torch.exp2(torch.tensor([2.0 - bits], device="cuda"))
+    hi = b + 4.0 - s
+    r = fq.philox_noise(x, None, seed=3, offset=4)
+
+    def run(fn, **kw):
+        xs = x.clone().requires_grad_(True)
+        s_, b_, h_ = s.clone().requires_grad_(True), b.clone().requires_grad_(True), hi.clone().requires_grad_(True)
+        y = fn(xs, s_, b_, b_, h_, method="STE", **kw)
+        y.backward(go)
+        return y.detach(), xs.grad, s_.grad, b_.grad, h_.grad
+    y_o, gx_o, gs_o, gb_o, gh_o = run(O.fake_quant, noise=r)
+    y_g, gx_g, gs_g, gb_g, gh_g = run(fq.fake_quant, philox=(3, 4))
+    assert torch.equal(y_g, y_o)
+    assert torch.equal(gx_g, gx_o)
+    del y_o, gx_o
+    # exact (fp64) value of the scale gradient from fp32 per-element terms
+    v = (torch.clamp(x, b, hi) - b) / s
+    e = torch.round(v) - v
+    inr = (x >= b) & (x <= hi)
+    exact_s = (go.double() * e.double()).sum() + ((3.0 ** -0.5) * (go * s)).double().mul(r.double()).sum()
+    exact_h = (go * s / s).double()[x > hi].sum()
+    _check_param_grad(gs_g, gs_o, exact_s.cpu().reshape(1), "g_scale", 1e-4)
+    _check_param_grad(gh_g, gh_o, exact_h.cpu().reshape(1), "g_hi", 1e-4)
+    # properties: codes in range and integral, clipped elements pass no gradient
+    _, codes, mm = fq.quantize_eval(x, s, b, b, hi, want_y=False, want_codes=True)
+    assert mm[0].item() >= 0 and mm[1].item() <= 2 ** bits - 1 and mm[2].item() == 0
+    assert torch.equal(codes, codes.round())
+    assert (gx_g[~inr] == 0).all()
+    # linearity of the backward in go (exact for a power-of-two factor)
+    xs = x.clone().requires_grad_(True)
+    y2 = fq.fake_quant(xs, s, b, b, hi, method="STE", philox=(3, 4))
+    y2.backward(go * 4.0)
+    assert torch.equal(xs.grad, gx_g * 4.0)

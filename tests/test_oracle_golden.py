@@ -1,0 +1,71 @@
+"""CPU: the oracle restatement vs vectors produced by the live reference
+(tests/golden/make_golden.py).  Forward / input gradients bit-exact; parameter
+gradients within 1e-6 relative (they are fp32 reductions whose order is the same
+ATen kernels here and there, so in practice they are identical too)."""
+import math
+
+import pytest
+import torch
+
+from oracle import fq_oracle as O
+from tests import helpers as H
+
+
+@pytest.mark.parametrize("name", H.golden_names("act_"))
+def test_act_golden(name):
+    c = H.load_golden(name)
+    r = H.run_act_case(c, O.fake_quant)
+    H.assert_bit_exact(r["y"], c["y"], "y")
+    H.assert_bit_exact(r["gx"], c["gx"], "gx")
+    for k in ("g_log_act_s", "g_log_act_q", "g_act_b"):
+        if k in c:
+            H.assert_close_rel(r[k], c[k], 1e-6, k, abs_floor=1e-7)
+    # two-call API + eval extras
+    s = torch.exp2(torch.tensor([float(c["log_act_s"])]))
+    q = torch.exp2(torch.tensor([float(c["log_act_q"])]))
+    b = torch.tensor([float(c["act_b"])])
+    codes = O.quantize(c["x"], s, b, b, b + q - s)
+    H.assert_bit_exact(codes, c["codes"], "codes")
+    O.check_codes(codes, s, b, b, b + q - s)
+    H.assert_bit_exact(O.act_bit_width(codes), c["bw"], "bw")
+
+
+@pytest.mark.parametrize("name", H.golden_names("w_"))
+def test_weight_golden(name):
+    c = H.load_golden(name)
+    r = H.run_weight_case(c, O.fake_quant)
+    H.assert_bit_exact(r["wq"], c["wq"], "wq")
+    H.assert_close_rel(r["g_weight"], c["g_weight"], 1e-6, "g_weight", abs_floor=1e-7)
+    H.assert_close_rel(r["g_log_wght_s"], c["g_log_wght_s"], 1e-6, "g_log_wght_s", abs_floor=1e-7)
+    if "bq" in c:
+        H.assert_bit_exact(r["bq"], c["bq"], "bq")
+        H.assert_close_rel(r["g_bias"], c["g_bias"], 1e-6, "g_bias", abs_floor=1e-7)
+
+
+def test_quantizer_codes_golden():
+    c = H.load_golden("quantizer_codes_lsq")
+    x = c["x"].clone().requires_grad_(True)
+    scale = c["scale"].clone().requires_grad_(True)
+    zp = c["zp"].clone().requires_grad_(True)
+    codes = O.quantize(x, scale, zp, -math.inf, math.inf, "LSQ")
+    codes.backward(c["gcodes"])
+    H.assert_bit_exact(codes, c["codes"], "codes")
+    H.assert_bit_exact(x.grad, c["gx"], "gx")
+    H.assert_close_rel(scale.grad, c["g_scale"], 1e-6, "g_scale", abs_floor=1e-7)
+    H.assert_close_rel(zp.grad, c["g_zp"], 1e-6, "g_zp", abs_floor=1e-7)
+
+
+def test_ewgs_intent_runs():
+    """The reference's QNEWGS cannot run (gdnsq.py:102); the oracle's restatement of its
+    intent must at least produce the documented closed form."""
+    torch.manual_seed(0)
+    v = (torch.randn(64) * 3).requires_grad_(True)
+    s = torch.tensor([0.5], requires_grad=True)
+    r = torch.randint(0, 2, (64,)).float() - 0.5
+    out = O._RoundNoise.apply(v, s, O.EWGS, r)
+    g = torch.randn(64)
+    out.backward(g)
+    e = torch.round(v.detach()) - v.detach()
+    # total grad to v = grad of (round(v) - v) path only here: -|g| * e * 0.01
+    assert torch.equal(v.grad, -torch.abs(g) * e * 1e-2)
+    torch.testing.assert_close(s.grad, ((3.0 ** -0.5) * g * r).sum().reshape(1))
