@@ -187,8 +187,7 @@ def run_ours(a):
     launches = {"n": 0}
 
     def step():
-        xs = x.requires_grad_(True)
-        xs.grad = None
+        xs = x.detach().requires_grad_(True)
         scale_p.grad = None
         y = mhaq_b200.fake_quant(xs, scale_p, zp, lo_, hi_, method=a.method)
         y.backward(go)
@@ -264,8 +263,7 @@ def run_ours(a):
         def e2e_step():
             dx.copy_(hx, non_blocking=True)
             dg.copy_(hg, non_blocking=True)
-            xs = dx.requires_grad_(True)
-            xs.grad = None
+            xs = dx.detach().requires_grad_(True)
             scale_p.grad = None
             y = mhaq_b200.fake_quant(xs, scale_p, zp, lo_, hi_, method=a.method)
             y.backward(dg)
@@ -310,8 +308,7 @@ def cpu_baseline(a, steps, warmup):
     sp = scale.clone().requires_grad_(True)
 
     def step():
-        xs = x.requires_grad_(True)
-        xs.grad = None
+        xs = x.detach().requires_grad_(True)
         sp.grad = None
         y = O.fake_quant(xs, sp, zp, lo_, hi_, method=a.method)
         y.backward(go)

@@ -139,6 +139,51 @@ __device__ __forceinline__ float f_sub(float a, float b) { return __fsub_rn(a, b
 __device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float f_div(float a, float b) { return __fdiv_rn(a, b); }
 
+// ---- exact division by a per-channel-invariant divisor ----------------------
+// The hot loops divide by the same scale `s` for every element of a channel, so
+// the reciprocal y = RN(1/s) is computed once (IEEE, __frcp_rn) and each
+// quotient is one multiply plus one Markstein correction, the remainder
+// r = a - q*s being evaluated EXACTLY by an FMA:
+//     q0 = RN(a*y);   q1 = RN(q0 + r0*y)   ==   RN(a/s)
+// for every a, s whose quotient and remainder stay in the normal range.
+// tools/verify_fastdiv.cu checks this (and the two-correction variant nvcc itself
+// emits for `/`) against __fdiv_rn over ALL 2^46 (significand(a), significand(s))
+// pairs plus the exponent corners of the guards: zero mismatches
+// (profiles/r01_fastdiv_exhaustive.txt).  3 instructions instead of ~10
+// (MUFU.RCP + 6 FFMA + FCHK + BSSY/BRA/BSYNC) per division.
+// The remainder is formed as q*s - a and negated on use, which keeps the sign of
+// a zero quotient (-0/s = -0) without extra instructions.  NaN propagates.
+// Out-of-range operands are the caller's job (see the guards in mhaq_fq.cu).
+__device__ __forceinline__ float div_exact(float a, float s, float y) {
+    const float q = __fmul_rn(a, y);
+    const float r = __fmaf_rn(q, s, -a);
+    return __fmaf_rn(-r, y, q);
+}
+// Two corrections (the textbook IEEE sequence); only used by the verifier.
+__device__ __forceinline__ float div_exact2(float a, float s, float y) {
+    float q = __fmul_rn(a, y);
+    float r = __fmaf_rn(q, s, -a);
+    q = __fmaf_rn(-r, y, q);
+    r = __fmaf_rn(q, s, -a);
+    return __fmaf_rn(-r, y, q);
+}
+// gu = RN(gv/s) when gv = RN(go*s): go itself is a faithful estimate of the
+// quotient, so ONE exact-remainder correction from it is correctly rounded
+// (checked exhaustively, same tool).  2 FMAs instead of a division.
+__device__ __forceinline__ float div_of_product(float go, float gv, float s, float y) {
+    const float r = __fmaf_rn(go, s, -gv);
+    return __fmaf_rn(-r, y, go);
+}
+// Ranges inside which the FMA sequences above are exact (no intermediate
+// under/overflow):  2^-32 <= s <= 2^32,  operand of a gradient division zero or
+// 2^-56 <= |go| (no upper bound needed: see DESIGN.md), forward input |x| <= 2^80.
+constexpr float kScaleLo = 2.3283064365386963e-10f;   // 2^-32
+constexpr float kScaleHi = 4294967296.0f;             // 2^32
+constexpr float kXHi = 1.2089258196146292e+24f;       // 2^80
+constexpr uint32_t kGoLoBits2m1 = (0x23800000u << 1) - 1u;   // (bits(2^-56) << 1) - 1
+constexpr float kGvHi = 1.2089258196146292e+24f;      // 2^80 (general gradient division)
+__device__ __forceinline__ bool scale_fast_ok(float s) { return s >= kScaleLo && s <= kScaleHi; }
+
 // torch.clamp(x, lo, hi): NaN in x propagates; lo > hi yields hi.
 __device__ __forceinline__ float f_clamp(float x, float lo, float hi) {
     float c = (x < lo) ? lo : x;

@@ -33,15 +33,34 @@ struct FwdStat {
     unsigned bad;
 };
 
+// General path: true IEEE division, any operand (also the ragged / unaligned tiles).
 __device__ __forceinline__ float fwd_elem(float x, const QConst &q, float &code) {
     float c = f_clamp(x, q.lo, q.hi);            // gdnsq.py:197
     float u = f_sub(c, q.zp);                    // gdnsq.py:199
     float v = f_div(u, q.s);                     // gdnsq.py:204
-    code = rintf(v);                             // v + (round(v) - v), gdnsq.py:15,208
+    float nz = f_sub(rintf(v), v);               // QNoise.forward, gdnsq.py:15
+    code = f_add(v, nz);                         // gdnsq.py:208 (== rint(v); NaN for v = +-inf)
     return f_add(f_mul(code, q.s), q.zp);        // gdnsq.py:229 (two roundings)
 }
+// Fast path: same roundings, the division by the channel-invariant scale done with the
+// hoisted reciprocal (bit-identical, see div_exact).  For |v| < 0.5 the value of v is
+// irrelevant to code = v + (rint(v) - v) = 0, so tiny / denormal u need no guard; huge
+// |x| (> 2^80, incl. inf) is sent to the general path by the caller.
+template <bool CLAMP>
+__device__ __forceinline__ float fwd_elem_fast(float x, const QConst &q, float rcp, float &code) {
+    const float c = CLAMP ? f_clamp(x, q.lo, q.hi) : x;
+    const float u = f_sub(c, q.zp);
+    const float v = div_exact(u, q.s, rcp);
+    const float nz = f_sub(rintf(v), v);
+    code = f_add(v, nz);
+    return f_add(f_mul(code, q.s), q.zp);
+}
 
-template <bool VEC>
+__device__ __forceinline__ float absmax4(float m, const float4 &v) {
+    return fmaxf(fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
+}
+
+template <bool VEC, bool CLAMP>
 __global__ void __launch_bounds__(kThreads)
 fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restrict__ codes,
               QParams prm, Geom g, double *__restrict__ mm_ws) {
@@ -50,6 +69,8 @@ fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restr
     for (int64_t t = blockIdx.x; t < g.n_tasks; t += gridDim.x) {
         const Task k = make_task(g, t);
         const QConst q = load_qconst(prm, k.ch);
+        const float rcp = __frcp_rn(q.s);
+        const bool fast_ok = VEC && scale_fast_ok(q.s) && (mm_ws == nullptr);
         const float *xr = x + k.row_off;
         float *yr = y ? y + k.row_off : nullptr;
         float *cr = codes ? codes + k.row_off : nullptr;
@@ -57,7 +78,41 @@ fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restr
         for (int64_t sub = k.q0; sub < k.q1; ++sub) {
             const int64_t base = sub * kSubElems + tid * 4;
             const bool full = (sub + 1) * kSubElems <= g.n_inner;
+            if (fast_ok && full) {
+                // ---------------- fast path: full, aligned sub-tile ----------------
 #pragma unroll
+                for (int b = 0; b < kSubIters / kU; ++b) {
+                    float4 xv[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u)
+                        xv[u] = ld_stream4(xr + base + (b * kU + u) * kIterElems);
+                    float mx = 0.f;
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) mx = absmax4(mx, xv[u]);
+                    const bool huge = mx > kXHi;      // NaN never sets it; NaN is fine on the fast path
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        float4 cv, yv;
+                        if (!huge) {
+                            yv.x = fwd_elem_fast<CLAMP>(xv[u].x, q, rcp, cv.x);
+                            yv.y = fwd_elem_fast<CLAMP>(xv[u].y, q, rcp, cv.y);
+                            yv.z = fwd_elem_fast<CLAMP>(xv[u].z, q, rcp, cv.z);
+                            yv.w = fwd_elem_fast<CLAMP>(xv[u].w, q, rcp, cv.w);
+                        } else {
+                            yv.x = fwd_elem(xv[u].x, q, cv.x);
+                            yv.y = fwd_elem(xv[u].y, q, cv.y);
+                            yv.z = fwd_elem(xv[u].z, q, cv.z);
+                            yv.w = fwd_elem(xv[u].w, q, cv.w);
+                        }
+                        const int64_t p = base + (b * kU + u) * kIterElems;
+                        if (yr) st_stream4(yr + p, yv);
+                        if (cr) st_stream4(cr + p, cv);
+                    }
+                }
+                continue;
+            }
+            // ---------------- general path: ragged / unaligned / eval statistics ----------------
+#pragma unroll 1
             for (int b = 0; b < kSubIters / kU; ++b) {
                 float4 xv[kU];
                 int nv[kU];
@@ -150,7 +205,7 @@ fq_minmax_finalize_kernel(const double *__restrict__ ws, int64_t n_tasks, float 
 // Backward
 // ===========================================================================
 struct Acc {
-    float se;  // sum go*e (+ estimator correction)  -> d/d scale via dequant-mul and div
+    float se;  // sum [go*code - gv*((u/s)/s)]        -> d/d scale via dequant-mul and div
     float sn;  // estimator's own scale gradient (GDNSQ noise term / LSQ)
     float sz;  // sum (go - g_u)                      -> d/d zero_point
     float sl;  // sum g_u [x < lo]                    -> d/d min_val
@@ -159,14 +214,31 @@ struct Acc {
 
 struct BwdConst {
     float smul;      // s (grad w.r.t. y) or 1 (grad w.r.t. codes)
-    float rs;        // 1/s, only used inside tolerance-checked sums
+    float rcp;       // RN(1/s) for the fast division sequences
     float delta;     // AEWGS per-channel delta
     bool codegrad;
     bool lo_lt_hi, lo_gt_hi;
 };
 
-template <int METHOD, bool CLAMP, int NOISE>
-__device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t bit,
+// The estimator: gradient w.r.t. v given g = gradient w.r.t. the codes (QN*.backward).
+template <int METHOD>
+__device__ __forceinline__ float estimator_gv(float g, float e, float delta) {
+    if (METHOD == MHAQ_FQ_STE || METHOD == MHAQ_FQ_LSQ) {
+        return __fmaf_rn(g, 0.f, g);                         // g + g*0   (gdnsq.py:50,78)
+    } else if (METHOD == MHAQ_FQ_EWGS) {
+        const float gi = f_mul(f_mul(-fabsf(g), e), kEwgsDelta);   // gdnsq.py:100
+        return f_add(g, gi);
+    } else {                                                 // AEWGS, gdnsq.py:118-141
+        const float sg = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);
+        const float nf = f_mul(sg, e);
+        float gs = f_mul(delta, nf);
+        gs = (gs > kAewgsCap) ? kAewgsCap : gs;              // clamp_max(1-gap)
+        return f_add(g, f_mul(-g, gs));
+    }
+}
+
+template <int METHOD, bool CLAMP, int NOISE, bool FAST>
+__device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t sign_flip,
                                           const QConst &q, const BwdConst &bc, Acc &acc) {
     // ---- recompute the forward (gdnsq.py:197-208) ----
     float c;
@@ -183,35 +255,32 @@ __device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t 
         in = (x == x);
     }
     const float u = f_sub(c, q.zp);
-    const float v = f_div(u, q.s);
-    const float code = rintf(v);
-    const float e = f_sub(code, v);                      // round(v) - v, exact
-    // ---- gradient w.r.t. codes, then the estimator (QN*.backward) ----
+    const float v = FAST ? div_exact(u, q.s, bc.rcp) : f_div(u, q.s);
+    const float e = f_sub(rintf(v), v);                  // round(v) - v, exact
+    const float code = f_add(v, e);
+    // ---- gradient w.r.t. codes, then the estimator ----
     const float g = f_mul(go, bc.smul);                  // MulBackward of code*s
-    float gi = 0.f, gv;
-    if (METHOD == MHAQ_FQ_STE || METHOD == MHAQ_FQ_LSQ) {
-        gv = __fmaf_rn(g, 0.f, g);                       // g + g*0   (gdnsq.py:50,78)
-    } else if (METHOD == MHAQ_FQ_EWGS) {
-        gi = f_mul(f_mul(-fabsf(g), e), kEwgsDelta);     // gdnsq.py:100
-        gv = f_add(g, gi);
-    } else {                                             // AEWGS, gdnsq.py:118-141
-        const float sg = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);
-        const float nf = f_mul(sg, e);
-        float gs = f_mul(bc.delta, nf);
-        gs = (gs > kAewgsCap) ? kAewgsCap : gs;          // clamp_max(1-gap)
-        gi = f_mul(-g, gs);
-        gv = f_add(g, gi);
+    const float gv = estimator_gv<METHOD>(g, e, bc.delta);
+    float gu;                                            // DivBackward (self): gv / s
+    if (!FAST) {
+        gu = f_div(gv, q.s);
+    } else if ((METHOD == MHAQ_FQ_STE || METHOD == MHAQ_FQ_LSQ) && !bc.codegrad) {
+        gu = div_of_product(go, gv, q.s, bc.rcp);        // gv == RN(go*s) (or NaN)
+    } else {
+        gu = div_exact(gv, q.s, bc.rcp);
     }
-    const float gu = f_div(gv, q.s);                     // DivBackward (self)
     const float gx = in ? gu : 0.f;                      // ClampBackward
     // ---- parameter-gradient partial sums ----
+    // d/ds: the reference's own fp32 per-element terms — MulBackward go*code and
+    // DivBackward -gv*((u/s)/s) — differenced per element (they nearly cancel, so the
+    // difference is all but exact) and only then accumulated: same terms as the
+    // reference, summed without its catastrophic cancellation between two big fp32 sums.
+    const float t2 = f_mul(gv, FAST ? div_exact(v, q.s, bc.rcp) : f_div(v, q.s));
     if (!bc.codegrad) {
-        acc.se = __fmaf_rn(go, e, acc.se);               // go*code - g*(v/s) = go*(code-v)
-        if (METHOD == MHAQ_FQ_EWGS || METHOD == MHAQ_FQ_AEWGS)
-            acc.se = __fmaf_rn(-gi, f_mul(v, bc.rs), acc.se);
+        acc.se += f_sub(f_mul(go, code), t2);
         acc.sz += f_sub(go, gu);                         // (+zp of dequant) - (sub zp)
     } else {
-        acc.se = __fmaf_rn(-gv, f_mul(v, bc.rs), acc.se);
+        acc.se -= t2;
         acc.sz -= gu;
     }
     if (METHOD == MHAQ_FQ_LSQ) {
@@ -220,7 +289,7 @@ __device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t 
         acc.sn += f_mul(f_mul(kInvSqrt3, g), rv);        // gdnsq.py:54-55
     } else {
         const float t = f_mul(kInvSqrt3, g);
-        const float ts = __uint_as_float(__float_as_uint(t) ^ ((bit ^ 1u) << 31));
+        const float ts = __uint_as_float(__float_as_uint(t) ^ (sign_flip & 0x80000000u));
         acc.sn = __fmaf_rn(ts, 0.5f, acc.sn);            // r = bit - 0.5
     }
     if (CLAMP) {
@@ -228,6 +297,25 @@ __device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t 
         acc.sh += hi_m ? gu : 0.f;
     }
     return gx;
+}
+
+// Exact input gradient for one element, true divisions (guard fall-back of the fast path).
+template <int METHOD, bool CLAMP>
+__device__ __noinline__ float gx_exact(float x, float go, QConst q, float smul, float delta) {
+    const float c = CLAMP ? f_clamp(x, q.lo, q.hi) : x;
+    const bool in = CLAMP ? ((x >= q.lo) && (x <= q.hi)) : (x == x);
+    const float v = f_div(f_sub(c, q.zp), q.s);
+    const float e = f_sub(rintf(v), v);
+    const float gv = estimator_gv<METHOD>(f_mul(go, smul), e, delta);
+    return in ? f_div(gv, q.s) : 0.f;
+}
+
+// min over the 4 components of (bits<<1)-1: zero maps to 0xffffffff (never the minimum),
+// anything else orders by magnitude -> "smallest non-zero |go|" with 2 integer ops/element.
+__device__ __forceinline__ uint32_t nzmin4(uint32_t m, const float4 &v) {
+    const uint32_t a = (__float_as_uint(v.x) << 1) - 1u, b = (__float_as_uint(v.y) << 1) - 1u;
+    const uint32_t c = (__float_as_uint(v.z) << 1) - 1u, d = (__float_as_uint(v.w) << 1) - 1u;
+    return min(min(min(m, a), min(b, c)), d);
 }
 
 template <int METHOD, bool CLAMP, int NOISE, bool VEC>
@@ -241,6 +329,7 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
     PhiloxKey key = {0, 0, 0, 0};
     if (NOISE == NOISE_PHILOX) key = make_key(seed, offset, philox_dev);
     const int64_t supers_per_row = (g.n_inner + kSuperElems - 1) / kSuperElems;
+    constexpr bool kProductDiv = (METHOD == MHAQ_FQ_STE || METHOD == MHAQ_FQ_LSQ);
 
     for (int64_t t = blockIdx.x; t < g.n_tasks; t += gridDim.x) {
         const Task k = make_task(g, t);
@@ -248,7 +337,7 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
         BwdConst bc;
         bc.codegrad = codegrad != 0;
         bc.smul = bc.codegrad ? 1.f : q.s;
-        bc.rs = f_div(1.f, q.s);
+        bc.rcp = __frcp_rn(q.s);
         bc.lo_lt_hi = q.lo < q.hi;
         bc.lo_gt_hi = q.lo > q.hi;
         bc.delta = 0.f;
@@ -260,6 +349,7 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
             den = (den < kAewgsEps) ? kAewgsEps : den;       // clamp_min(eps)
             bc.delta = f_div(num, den);                      // gdnsq.py:134
         }
+        const bool fast_ok = VEC && scale_fast_ok(q.s);
         const float *xr = x + k.row_off;
         const float *gr = go + k.row_off;
         const float *rr = (NOISE == NOISE_EXPLICIT) ? r + k.row_off : nullptr;
@@ -279,7 +369,52 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
                     curT = T;
                 }
             }
+            if (fast_ok && full) {
+                // ---------------- fast path: full, aligned sub-tile ----------------
 #pragma unroll
+                for (int b = 0; b < kSubIters / kU; ++b) {
+                    float4 xv[kU], gv[kU], rv4[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int64_t p = base + (b * kU + u) * kIterElems;
+                        xv[u] = ld_stream4(xr + p);
+                        gv[u] = ld_stream4(gr + p);
+                        rv4[u] = (NOISE == NOISE_EXPLICIT) ? ld_stream4(rr + p)
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    // guard of the gradient division: smallest non-zero |go| >= 2^-56
+                    // (and, off the product shortcut, largest |go| <= 2^80)
+                    uint32_t mn = 0xffffffffu;
+                    float mx = 0.f;
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        mn = nzmin4(mn, gv[u]);
+                        if (!kProductDiv || bc.codegrad) mx = absmax4(mx, gv[u]);
+                    }
+                    const bool odd = (mn < kGoLoBits2m1) || (mx > kGvHi);
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int64_t p = base + (b * kU + u) * kIterElems;
+                        uint32_t inv = 0;
+                        if (NOISE == NOISE_PHILOX) inv = ~noise_nibble(rnd, it0 + b * kU + u);
+                        float4 o;
+                        o.x = bwd_elem<METHOD, CLAMP, NOISE, true>(xv[u].x, gv[u].x, rv4[u].x, inv << 31, q, bc, acc);
+                        o.y = bwd_elem<METHOD, CLAMP, NOISE, true>(xv[u].y, gv[u].y, rv4[u].y, inv << 30, q, bc, acc);
+                        o.z = bwd_elem<METHOD, CLAMP, NOISE, true>(xv[u].z, gv[u].z, rv4[u].z, inv << 29, q, bc, acc);
+                        o.w = bwd_elem<METHOD, CLAMP, NOISE, true>(xv[u].w, gv[u].w, rv4[u].w, inv << 28, q, bc, acc);
+                        if (odd) {   // rare: tiny / huge gradients -> exact IEEE division for gx
+                            o.x = gx_exact<METHOD, CLAMP>(xv[u].x, gv[u].x, q, bc.smul, bc.delta);
+                            o.y = gx_exact<METHOD, CLAMP>(xv[u].y, gv[u].y, q, bc.smul, bc.delta);
+                            o.z = gx_exact<METHOD, CLAMP>(xv[u].z, gv[u].z, q, bc.smul, bc.delta);
+                            o.w = gx_exact<METHOD, CLAMP>(xv[u].w, gv[u].w, q, bc.smul, bc.delta);
+                        }
+                        if (gxr) st_stream4(gxr + p, o);
+                    }
+                }
+                continue;
+            }
+            // ---------------- general path: ragged / unaligned / out-of-range scale ----------------
+#pragma unroll 1
             for (int b = 0; b < kSubIters / kU; ++b) {
                 float4 xv[kU], gv[kU], rv4[kU];
                 int nv[kU];
@@ -297,13 +432,13 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
                 for (int u = 0; u < kU; ++u) {
                     if (!nv[u]) continue;
                     const int64_t p = base + (int64_t)(b * kU + u) * kIterElems;
-                    uint32_t nib = 0;
-                    if (NOISE == NOISE_PHILOX) nib = noise_nibble(rnd, it0 + b * kU + u);
+                    uint32_t inv = 0;
+                    if (NOISE == NOISE_PHILOX) inv = ~noise_nibble(rnd, it0 + b * kU + u);
                     float4 o;
-                    o.x = bwd_elem<METHOD, CLAMP, NOISE>(xv[u].x, gv[u].x, rv4[u].x, (nib >> 0) & 1u, q, bc, acc);
-                    o.y = bwd_elem<METHOD, CLAMP, NOISE>(xv[u].y, gv[u].y, rv4[u].y, (nib >> 1) & 1u, q, bc, acc);
-                    o.z = bwd_elem<METHOD, CLAMP, NOISE>(xv[u].z, gv[u].z, rv4[u].z, (nib >> 2) & 1u, q, bc, acc);
-                    o.w = bwd_elem<METHOD, CLAMP, NOISE>(xv[u].w, gv[u].w, rv4[u].w, (nib >> 3) & 1u, q, bc, acc);
+                    o.x = bwd_elem<METHOD, CLAMP, NOISE, false>(xv[u].x, gv[u].x, rv4[u].x, inv << 31, q, bc, acc);
+                    o.y = bwd_elem<METHOD, CLAMP, NOISE, false>(xv[u].y, gv[u].y, rv4[u].y, inv << 30, q, bc, acc);
+                    o.z = bwd_elem<METHOD, CLAMP, NOISE, false>(xv[u].z, gv[u].z, rv4[u].z, inv << 29, q, bc, acc);
+                    o.w = bwd_elem<METHOD, CLAMP, NOISE, false>(xv[u].w, gv[u].w, rv4[u].w, inv << 28, q, bc, acc);
                     if (gxr) store4<VEC>(gxr, p, g.n_inner, o);
                 }
             }
@@ -658,10 +793,13 @@ int mhaq_fq_fwd_f32(const float *x, float *y, float *codes, const float *scale, 
                      (!codes || aligned16(codes));
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(g.n_tasks);
-    if (vec)
-        fq_fwd_kernel<true><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+    const bool clamp = (lo != nullptr) || (hi != nullptr);
+    if (vec && clamp)
+        fq_fwd_kernel<true, true><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+    else if (vec)
+        fq_fwd_kernel<true, false><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
     else
-        fq_fwd_kernel<false><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+        fq_fwd_kernel<false, true><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
     return last_error();
 }
 

@@ -1,0 +1,144 @@
+"""Operator boundary of the GDNSQ quantizer — mirror of the reference's
+src/quantization/gdnsq/gdnsq.py:159-241 (class ``Quantizer``), backed by the
+sm_100a kernels.
+
+Same constructor, same mutable attributes (``scale, zero_point, min_val, max_val,
+qnmethod, module, rnoise_ratio, positive_scale``), same ``quantize`` /
+``dequantize`` semantics and eval-mode assertion messages.  New: ``fake_quant``,
+the fused ``dequantize(quantize(x))`` the layer wrappers call (one kernel each
+way instead of ~8 / ~19-27 ATen launches).
+
+The reference's ``QNoise`` / ``QNSTE`` / ``QNLSQ`` / ``QNEWGS`` / ``QNAEWGS``
+autograd Functions (gdnsq.py:11-147) have no separate existence here: their
+forward (``round(v) - v``) and backward are fused into ``mhaq_fq_fwd_f32`` /
+``mhaq_fq_bwd_f32``.  The names are kept importable; calling them raises.
+"""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from ... import ops
+from .gdnsq_utils import QMode, QNMethod  # noqa: F401
+
+
+def reduce_to_shape(t: Tensor, like: Tensor) -> Tensor:
+    """Mean over the dims where `like` has size 1 (reference gdnsq.py:150-152)."""
+    dims = tuple(i for i, n in enumerate(like.shape) if n == 1)
+    return torch.mean(t, dim=dims, keepdim=True)
+
+
+class _Fused:
+    """Placeholder for an autograd Function of the reference that is fused into the kernels."""
+
+    @classmethod
+    def apply(cls, *a, **k):
+        raise NotImplementedError(
+            f"{cls.__name__} is fused into the sm_100a kernels (mhaq_fq_fwd_f32 / mhaq_fq_bwd_f32); "
+            "use Quantizer.quantize / Quantizer.fake_quant")
+
+
+class QNoise(_Fused):
+    pass
+
+
+class QNSTE(QNoise):
+    pass
+
+
+class QNLSQ(QNoise):
+    pass
+
+
+class QNEWGS(QNoise):
+    pass
+
+
+class QNAEWGS(QNoise):
+    pass
+
+
+def scaled_noise(x, s):
+    return QNoise.apply(x, s)
+
+
+class Quantizer:
+    def __init__(self, module, scale, zero_point, min_val, max_val,
+                 rnoise_ratio=torch.Tensor([-1.0]), qnmethod: QNMethod = QNMethod.STE) -> None:
+        self.module = module
+        self.scale = scale
+        self.zero_point = zero_point
+        self.min_val = min_val
+        self.max_val = max_val
+        self.rnoise_ratio = torch.Tensor([rnoise_ratio])       # vestigial (gdnsq.py:185)
+        # evaluated once at construction, exactly like the reference (gdnsq.py:186)
+        self.positive_scale = torch.all(torch.as_tensor(self.scale) > 0).item()
+        self.qnmethod = qnmethod
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _method(self):
+        if not isinstance(self.qnmethod, QNMethod):
+            raise AttributeError(f"Unknown method {self.qnmethod}!")
+        return self.qnmethod
+
+    def _zp_like(self, value):
+        zp = self.zero_point
+        if not torch.is_tensor(zp):
+            zp = torch.full((1,), float(zp), dtype=value.dtype, device=value.device)
+        return zp
+
+    # -- reference API ---------------------------------------------------------------------
+    def quantize(self, value):
+        """Clamp, shift, scale, round: integer-valued codes (gdnsq.py:189-219)."""
+        if not self.positive_scale:                            # gdnsq.py:201-202
+            return torch.clamp(value, min=self.min_val, max=self.max_val) - self.zero_point
+        method = self._method()
+        training = self.module.training
+        if training or torch.is_grad_enabled() and value.requires_grad:
+            codes = ops.quantize_codes(value, self.scale, self._zp_like(value), self.min_val,
+                                       self.max_val, method=method)
+            if training:
+                return codes
+            self._assert_valid(ops.quantize_eval(value, self.scale, self._zp_like(value),
+                                                 self.min_val, self.max_val, want_y=False)[2])
+            return codes
+        _, codes, mm = ops.quantize_eval(value, self.scale, self._zp_like(value), self.min_val,
+                                         self.max_val, want_y=False, want_codes=True)
+        self._last_minmax = mm
+        self._assert_valid(mm)
+        return codes
+
+    @staticmethod
+    def _assert_valid(mm):
+        """Eval-mode assertions of gdnsq.py:211-217.  Codes are rint() of a clamped value, so
+        they are integral and inside [floor((min-zp)/s), ceil((max-zp)/s)] by construction
+        unless non-finite; the kernel counts non-finite codes in the same pass (one host
+        sync instead of the reference's three)."""
+        if mm is not None and float(mm[2].item()) != 0.0:
+            raise AssertionError("Not all elements in the tensor have integer values.")
+
+    def dequantize(self, quantized_value):
+        """codes * scale + zero_point (gdnsq.py:221-229) — the two-call form; the layers use
+        fake_quant()."""
+        if not self.positive_scale:
+            return quantized_value + self.zero_point
+        return quantized_value * self.scale + self.zero_point
+
+    def _get_rnoise(self, value: Tensor, scale: Tensor):
+        self._method()
+        return QNoise.apply(value, scale)
+
+    # -- fused entry -----------------------------------------------------------------------
+    def fake_quant(self, value, noise=None):
+        """dequantize(quantize(value)) in one kernel each way."""
+        if not self.positive_scale:
+            return torch.clamp(value, min=self.min_val, max=self.max_val)
+        return ops.fake_quant(value, self.scale, self._zp_like(value), self.min_val, self.max_val,
+                              method=self._method(), noise=noise)
+
+    def fake_quant_eval(self, value):
+        """No-grad fused forward that also yields (min code, max code, #non-finite) — the
+        eval extras of gdnsq.py:211-217 / gdnsq_act.py:51-54 without extra passes."""
+        y, _, mm = ops.quantize_eval(value, self.scale, self._zp_like(value), self.min_val,
+                                     self.max_val, want_y=True, want_codes=False)
+        return y, mm

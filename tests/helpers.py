@@ -34,28 +34,15 @@ def bits_to_noise(bits):
     return None if bits is None else bits.float() - 0.5
 
 
-def assert_bit_exact(a, b, what=""):
-    """Numerically identical including NaN positions (signed zeros compare equal)."""
-    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
-    a, b = a.detach().cpu(), b.detach().cpu()
-    same = (a == b) | (torch.isnan(a) & torch.isnan(b))
-    if not bool(same.all()):
-        bad = (~same).nonzero()
-        i = tuple(bad[0].tolist())
-        raise AssertionError(f"{what}: {int((~same).sum())}/{a.numel()} elements differ; "
-                             f"first at {i}: {a[i].item()!r} vs {b[i].item()!r}")
+from oracle.checks import assert_bit_exact, assert_close_rel, assert_param_grad  # noqa: E402,F401
 
 
-def assert_close_rel(a, b, rel, what="", abs_floor=0.0):
-    """|a-b| <= rel*|b| + abs_floor elementwise (b is the reference)."""
-    a, b = a.detach().cpu().double().reshape(-1), b.detach().cpu().double().reshape(-1)
-    assert a.shape == b.shape, f"{what}: shape mismatch"
-    err = (a - b).abs()
-    tol = rel * b.abs() + abs_floor
-    if not bool((err <= tol).all()):
-        i = int((err - tol).argmax())
-        raise AssertionError(f"{what}: |{a[i].item():.9g} - {b[i].item():.9g}| = {err[i].item():.3g} "
-                             f"> {tol[i].item():.3g} (rel {rel})")
+def _pin_to_cpu_value(t, log_t):
+    """exp2 is parameter preparation OUTSIDE the kernels and is done by torch on either
+    device; CUDA's exp2f and the CPU's vectorised exp2 may differ in the last bit, so when
+    comparing a CUDA run with CPU-generated fixtures give the CUDA graph the CPU value."""
+    if t.is_cuda:
+        t.data.copy_(torch.exp2(log_t.detach().cpu()))
 
 
 # ---------------------------------------------------------------------------
@@ -70,6 +57,8 @@ def run_act_case(c, fq, device="cpu"):
     act_b = torch.tensor([float(c["act_b"])], device=device, requires_grad=c["signed"])
     s = torch.exp2(log_s)
     q = torch.exp2(log_q)
+    _pin_to_cpu_value(s, log_s)
+    _pin_to_cpu_value(q, log_q)
     y = fq(x, s, act_b, act_b, act_b + q - s, method="STE", noise=bits_to_noise(c["noise_bits"]).to(device))
     y.backward(c["go"].to(device))
     return dict(y=y, gx=x.grad, g_log_act_s=log_s.grad, g_log_act_q=log_q.grad,
@@ -81,6 +70,7 @@ def run_weight_case(c, fq, device="cpu"):
     w = c["weight"].to(device).clone().requires_grad_(True)
     log_s = c["log_wght_s"].to(device).clone().requires_grad_(True)
     s = torch.exp2(log_s)
+    _pin_to_cpu_value(s, log_s)
     zp = w.amin((1, 2, 3), keepdim=True) if c["per_channel"] else w.amin()
     noise = bits_to_noise(c.get("noise_bits"))
     wq = fq(w, s, zp, -math.inf, math.inf, method=c["method"],
@@ -98,3 +88,23 @@ def run_weight_case(c, fq, device="cpu"):
     if "bq" in c:
         out["g_bias"] = b.grad
     return out
+
+
+def exact_act_param_grads(c):
+    """fp64 sums of the reference's fp32 per-element terms, chained to the log-params in
+    fp64 (gdnsq_act.py:42-48): the value both fp32 implementations approximate."""
+    import math as _m
+    x = c["x"]
+    sv = torch.exp2(torch.tensor([float(c["log_act_s"])]))
+    qv = torch.exp2(torch.tensor([float(c["log_act_q"])]))
+    bv = torch.tensor([float(c["act_b"])])
+    full = lambda t: t.expand(x.shape).contiguous().requires_grad_(True)
+    s_, z_, l_, h_ = full(sv), full(bv), full(bv), full((bv + qv) - sv)
+    y = O.fake_quant(x, s_, z_, l_, h_, "STE", bits_to_noise(c["noise_bits"]))
+    y.backward(c["go"])
+    gS, gZ, gL, gH = (t.grad.double().sum() for t in (s_, z_, l_, h_))
+    ln2 = _m.log(2.0)
+    return dict(g_log_act_s=((gS - gH) * sv.double() * ln2).reshape(1),
+                g_log_act_q=(gH * qv.double() * ln2).reshape(1),
+                g_act_b=(gZ + gL + gH).reshape(1))
+
