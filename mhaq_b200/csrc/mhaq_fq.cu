@@ -243,7 +243,14 @@ __device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t 
     // ---- recompute the forward (gdnsq.py:197-208) ----
     float c;
     bool in, lo_m = false, hi_m = false;
-    if (CLAMP) {
+    if (CLAMP && FAST) {
+        // fast path is only entered with lo < hi: the clamp_backward_min_max predicate is
+        // then constant-true and the masks collapse to the two comparisons
+        lo_m = x < q.lo;
+        hi_m = x > q.hi;
+        c = hi_m ? q.hi : (lo_m ? q.lo : x);
+        in = (c == x);                                   // == (x >= lo && x <= hi); false for NaN
+    } else if (CLAMP) {
         const bool p_lt = x < q.lo, p_gt = x > q.hi;
         const float c1 = p_lt ? q.lo : x;
         c = (c1 > q.hi) ? q.hi : c1;
@@ -293,8 +300,8 @@ __device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t 
         acc.sn = __fmaf_rn(ts, 0.5f, acc.sn);            // r = bit - 0.5
     }
     if (CLAMP) {
-        acc.sl += lo_m ? gu : 0.f;
-        acc.sh += hi_m ? gu : 0.f;
+        if (lo_m) acc.sl += gu;
+        if (hi_m) acc.sh += gu;
     }
     return gx;
 }
@@ -349,7 +356,7 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
             den = (den < kAewgsEps) ? kAewgsEps : den;       // clamp_min(eps)
             bc.delta = f_div(num, den);                      // gdnsq.py:134
         }
-        const bool fast_ok = VEC && scale_fast_ok(q.s);
+        const bool fast_ok = VEC && scale_fast_ok(q.s) && (!CLAMP || bc.lo_lt_hi);
         const float *xr = x + k.row_off;
         const float *gr = go + k.row_off;
         const float *rr = (NOISE == NOISE_EXPLICIT) ? r + k.row_off : nullptr;

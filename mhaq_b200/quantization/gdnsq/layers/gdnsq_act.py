@@ -1,0 +1,57 @@
+"""``NoisyAct`` — activation quantizer wrapper; mirror of the reference's
+src/quantization/gdnsq/layers/gdnsq_act.py:9-55 on the sm_100a kernels.
+
+Same constructor arguments, parameters (``log_act_s, log_act_q, act_b`` each
+``(1,)``; ``act_b`` trainable iff ``signed``), initial values and ``bw`` attribute.
+The parameter preparation (``exp2``, ``act_b + q - s``) stays in PyTorch so autograd
+chains the log-domain gradients exactly as in the reference; the tensor-sized work
+is one fused kernel each way.
+"""
+import torch
+from torch import nn, inf
+
+from ..gdnsq import Quantizer
+from ..gdnsq_utils import QNMethod
+
+
+class NoisyAct(nn.Module):
+    def __init__(self, init_s=-10, init_q=10, signed=True, noise_ratio=1, disable=False,
+                 qnmethod: QNMethod = QNMethod.STE) -> None:
+        super().__init__()
+        self.disable = disable
+        self.signed = signed
+        zero_point = 0.0 if not signed else -torch.exp2(torch.tensor(init_q - 1).float())
+        self._act_b = torch.tensor([zero_point]).float()
+        self._log_act_s = torch.tensor([init_s]).float()
+        self._log_act_q = torch.tensor([init_q]).float()
+        self._noise_ratio = torch.tensor(noise_ratio)
+        self.log_act_q = torch.nn.Parameter(self._log_act_q, requires_grad=True)
+        self.act_b = torch.nn.Parameter(self._act_b, requires_grad=bool(signed))
+        self.log_act_s = torch.nn.Parameter(self._log_act_s, requires_grad=True)
+        self.Q = Quantizer(self, torch.exp2(self._log_act_s), 0, -inf, inf, qnmethod=qnmethod)
+        self.bw = torch.tensor(0.0)
+
+    def forward(self, x):
+        if self.disable:
+            return x
+        s = torch.exp2(self.log_act_s)
+        q = torch.exp2(self.log_act_q)
+
+        self.Q.zero_point = self.act_b
+        self.Q.min_val = self.act_b
+        self.Q.max_val = self.act_b + q - s
+        self.Q.scale = s
+
+        if self.training:
+            return self.Q.fake_quant(x)
+        # eval: the reference quantizes, asserts (3 host syncs), takes aminmax of the codes and
+        # dequantizes (gdnsq_act.py:50-55); here one pass yields y and (min, max, #bad) codes
+        needs_graph = torch.is_grad_enabled() and (
+            x.requires_grad or any(p.requires_grad for p in (self.log_act_s, self.log_act_q, self.act_b)))
+        with torch.no_grad():
+            y, mm = self.Q.fake_quant_eval(x)
+        self.Q._assert_valid(mm)
+        self.bw = torch.log2(mm[1] - mm[0] + 1)
+        if needs_graph:
+            return self.Q.fake_quant(x)
+        return y

@@ -1,0 +1,82 @@
+"""``NoisyConv2d`` — weight-quantizing convolution; mirror of the reference's
+src/quantization/gdnsq/layers/gdnsq_conv2d.py:13-119 on the sm_100a kernels.
+
+Same constructor, parameters and state-dict layout: ``log_wght_s`` is ``(1,)``
+(per-tensor) or ``(O,1,1,1)`` (per-channel); ``log_b_s`` ``(1,)`` exists only
+per-channel and — exactly as in the reference — is never used (bias quantization
+reuses the weight scale / row minimum, gdnsq_conv2d.py:86-94); ``_noise_ratio`` is
+a non-trainable ``(1,)`` Parameter kept for state-dict compatibility.
+"""
+from typing import Tuple
+
+import torch
+from torch import nn, inf
+
+from ....aux.types import QScheme
+from ....aux.qutils import is_biased
+from ..gdnsq import Quantizer
+from ..gdnsq_utils import QNMethod
+from ._wcache import WeightQuantCache
+
+
+class NoisyConv2d(nn.Conv2d):
+    def __init__(self, in_channels: int, out_channels: int, kernel_size, stride=1, padding=0,
+                 dilation=1, groups: int = 1, bias: bool = True, padding_mode: str = "zeros",
+                 device=None, dtype=None, qscheme: QScheme = QScheme.PER_TENSOR,
+                 log_s_init: float = -12, rand_noise: bool = False, quant_bias: bool = False,
+                 qnmethod: QNMethod = QNMethod.AEWGS) -> None:
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups,
+                         bias, padding_mode, device, dtype)
+        self.qscheme = qscheme
+        if self.qscheme == QScheme.PER_TENSOR:
+            self.log_wght_s = nn.Parameter(torch.Tensor([log_s_init]), requires_grad=True)
+        elif self.qscheme == QScheme.PER_CHANNEL:
+            self.log_wght_s = nn.Parameter(torch.empty((out_channels, 1, 1, 1)).fill_(log_s_init),
+                                           requires_grad=True)
+            self.log_b_s = nn.Parameter(torch.empty(1).fill_(log_s_init), requires_grad=True)
+        self._noise_ratio = torch.nn.Parameter(torch.Tensor([1]), requires_grad=False)
+        self.Q = Quantizer(self, torch.exp2(self.log_wght_s), 0, -inf, inf, qnmethod=qnmethod)
+        self.rand_noise = rand_noise
+        self.quant_bias = quant_bias
+        if self.quant_bias:
+            self.Q_b = Quantizer(self, torch.exp2(self.log_b_s), 0, -inf, inf, qnmethod=qnmethod)
+        self._wq_cache = WeightQuantCache()
+
+    def quantized_weight(self):
+        """(weight_q, bias_q) — computed once per parameter version (see _wcache)."""
+        key, hit = self._wq_cache.lookup((self.weight, self.log_wght_s, self.bias),
+                                         torch.is_grad_enabled(), self.training)
+        if hit is not None:
+            return hit
+        s = torch.exp2(self.log_wght_s)
+        self.Q.scale = s
+        if self.qscheme == QScheme.PER_CHANNEL:
+            mn = self.weight.amin((1, 2, 3), keepdim=True)
+        elif self.qscheme == QScheme.PER_TENSOR:
+            mn = self.weight.amin()
+        self.Q.zero_point = mn
+
+        if self.quant_bias:
+            self.Q_b.scale = s.ravel()
+            self.Q_b.zero_point = mn.ravel()
+            bias = self.Q_b.fake_quant(self.bias)
+        else:
+            bias = self.bias
+        weight = self.Q.fake_quant(self.weight)
+        # the cache holds the weight only; a quantized bias (tiny) is recomputed per call
+        # so that one cache entry never pins two autograd graphs
+        if not self.quant_bias:
+            self._wq_cache.store(key, (weight, bias))
+        return weight, bias
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        weight, bias = self.quantized_weight()
+        return self._conv_forward(input, weight, bias)
+
+    def extra_repr(self) -> str:
+        noise_ratio = self._noise_ratio if self.rand_noise else torch.zeros_like(self._noise_ratio)
+        return (f"in_channels={self.in_channels}, out_channels={self.out_channels}, "
+                f"kernel_size={self.kernel_size},\nstride={self.stride}, padding={self.padding}, "
+                f"dilation={self.dilation},\ngroups={self.groups}, bias={is_biased(self)}, "
+                f"log_wght_s_mean={self.log_wght_s.mean()},\nnoise_ratio={noise_ratio}, "
+                f"quantized_bias={self.quant_bias}")

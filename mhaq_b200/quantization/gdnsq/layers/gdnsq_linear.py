@@ -1,0 +1,61 @@
+"""``NoisyLinear`` — weight-quantizing linear layer; mirror of the reference's
+src/quantization/gdnsq/layers/gdnsq_linear.py:13-95 on the sm_100a kernels.
+
+State-dict layout as in the reference: ``log_wght_s`` is ``(1,)`` (per-tensor) or
+``(out_features,1,1,1)`` (per-channel, gdnsq_linear.py:54-58).  The reference's
+per-channel forward calls ``weight.amin((1,2,3))`` on a 2-D weight and therefore
+cannot run (gdnsq_linear.py:71); here the per-channel scale is
+viewed as ``(out_features, 1)`` and the row minimum taken over dim 1 — the evident
+intent, same numbers the conv path produces for a 1x1 kernel.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn, inf
+
+from ....aux.types import QScheme
+from ....aux.qutils import is_biased
+from ..gdnsq import Quantizer
+from ..gdnsq_utils import QNMethod
+from ._wcache import WeightQuantCache
+
+
+class NoisyLinear(nn.Linear):
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None,
+                 dtype=None, qscheme: QScheme = QScheme.PER_TENSOR, log_s_init: float = -12,
+                 rand_noise: bool = False, qnmethod: QNMethod = QNMethod.STE) -> None:
+        super().__init__(in_features, out_features, bias, device, dtype)
+        self.qscheme = qscheme
+        if self.qscheme == QScheme.PER_TENSOR:
+            self.log_wght_s = nn.Parameter(torch.Tensor([log_s_init]), requires_grad=True)
+        elif self.qscheme == QScheme.PER_CHANNEL:
+            self.log_wght_s = nn.Parameter(torch.empty((out_features, 1, 1, 1)).fill_(log_s_init),
+                                           requires_grad=True)
+        self._noise_ratio = nn.Parameter(torch.Tensor([1]), requires_grad=False)
+        self.Q = Quantizer(self, torch.exp2(self.log_wght_s), 0, -inf, inf, qnmethod=qnmethod)
+        self.rand_noise = rand_noise
+        self._wq_cache = WeightQuantCache()
+
+    def quantized_weight(self):
+        key, hit = self._wq_cache.lookup((self.weight, self.log_wght_s), torch.is_grad_enabled(),
+                                         self.training)
+        if hit is not None:
+            return hit
+        if self.qscheme == QScheme.PER_CHANNEL:
+            s = torch.exp2(self.log_wght_s).reshape(self.out_features, 1)
+            mn = self.weight.amin(1, keepdim=True)
+        else:
+            s = torch.exp2(self.log_wght_s)
+            mn = self.weight.amin()
+        self.Q.scale = s
+        self.Q.zero_point = mn
+        weight = self.Q.fake_quant(self.weight)
+        self._wq_cache.store(key, weight)
+        return weight
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        return F.linear(input, self.quantized_weight(), self.bias)
+
+    def extra_repr(self) -> str:
+        noise_ratio = self._noise_ratio if self.rand_noise else torch.zeros_like(self._noise_ratio)
+        return (f"in_features={self.in_features}, out_features={self.out_features}, "
+                f"bias={is_biased(self)},\nlog_wght_s={self.log_wght_s}, noise_ratio={noise_ratio}")
