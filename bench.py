@@ -5,7 +5,7 @@
     python bench.py --impl reference [...]                        # reference CPU path (oracle port)
 
 A "step" is one pass of the hot path over one batch of synthetic input: one
-fake-quant forward + one backward (incl. the deterministic finalize) over a
+fake-quant forward + one backward (incl. the in-kernel deterministic reduction) over a
 [C, N/C] fp32 tensor.  Default workload = BASELINE.json configs[1] headline
 point: per-channel (C=512) N=2^28 elements, GDNSQ/STE estimator with fused
 Philox noise, 4 bits.  GB/s = 20 B/element (8 fwd + 12 bwd) x N / t.
@@ -191,7 +191,7 @@ def run_ours(a):
         scale_p.grad = None
         y = mhaq_b200.fake_quant(xs, scale_p, zp, lo_, hi_, method=a.method)
         y.backward(go)
-        launches["n"] += 3 + (2 if a.method == "AEWGS" else 0)
+        launches["n"] += 3 + (2 if a.method == "AEWGS" else 0)   # fwd + bwd + finalize (+ AEWGS stats x2)
         return y, xs.grad, scale_p.grad
 
     for _ in range(max(a.warmup, 3)):
@@ -232,7 +232,7 @@ def run_ours(a):
                 traffic = json.load(open(tp)).get("fq_bwd_kernel_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "fq_bwd_kernel (+finalize)", "achieved": round(ach_b, 1),
+        roofline = {"bound": "hbm", "kernel": "fq_bwd_kernel (+ deterministic finalize)", "achieved": round(ach_b, 1),
                     "peak": peak, "unit": "GB/s", "frac": round(ach_b / peak, 4), "traffic": traffic,
                     "peak_source": peak_src, "frac_of_8TBps_nominal": round(ach_b / 8000.0, 4),
                     "bytes_per_elem": bwd_bytes, "ms_per_launch": round(t_b, 4),

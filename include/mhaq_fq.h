@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define MHAQ_FQ_ABI_VERSION 1
+#define MHAQ_FQ_ABI_VERSION 2
 
 /* gradient estimators — numeric values follow the reference enum
  * QNMethod (src/quantization/gdnsq/gdnsq_utils.py:9-13). */
@@ -60,16 +60,22 @@ extern "C" {
 #define MHAQ_FQ_EINVAL (-1)
 #define MHAQ_FQ_ENULL (-2)
 
-/* doubles per task in the backward / stats workspace */
+/* doubles per record in the backward / stats workspace */
 #define MHAQ_FQ_NPART 8
 
 int mhaq_fq_abi_version(void);
 const char *mhaq_fq_build_info(void);
 
-/* Number of workspace "tasks" the kernels use for a [n_rows][n_inner] tensor.
- * Workspace size in bytes = tasks * MHAQ_FQ_NPART * sizeof(double). */
+/* Workspaces (caller-owned device memory) for a [n_rows][n_inner] tensor:
+ *   ws      : mhaq_fq_workspace_bytes() bytes of scratch, contents irrelevant.
+ *   tickets : mhaq_fq_ticket_count() unsigned ints used by the deterministic finalize.
+ *             They MUST be zero on entry; the kernel leaves them zero again, so one
+ *             zero-initialised buffer can be reused forever by calls that are ordered on
+ *             one stream (allocate one per stream).
+ * mhaq_fq_num_tasks: number of records the streaming kernels write (informational). */
 int64_t mhaq_fq_num_tasks(int64_t n_rows, int64_t n_inner);
 int64_t mhaq_fq_workspace_bytes(int64_t n_rows, int64_t n_inner);
+int64_t mhaq_fq_ticket_count(int64_t n_rows, int64_t n_inner, int64_t n_ch);
 
 /* Forward: y = rint((clamp(x,lo,hi) - zp) / s) * s + zp, each step one IEEE
  * fp32 rounding (no FMA contraction, true division, round-half-even).
@@ -89,7 +95,8 @@ int mhaq_fq_fwd_f32(const float *x, float *y, float *codes,
 int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_inner,
                             float *out3, void *stream);
 
-/* Backward of the fake-quant op.
+/* Backward of the fake-quant op: input gradient plus one fp64 record of partial
+ * parameter-gradient sums per task (fp32 per thread -> warp shuffle -> fp64 per CTA).
  *   go      : gradient w.r.t. y (go_is_code_grad=0) or w.r.t. the codes
  *             returned by quantize() (go_is_code_grad=1)
  *   x       : the forward input (the only tensor saved for backward)
@@ -100,8 +107,7 @@ int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_i
  *             if philox_dev != NULL the kernel reads seed=philox_dev[0] and
  *             adds philox_dev[1] to offset (CUDA-graph friendly).
  *   aewgs_stats : [3*n_ch] per-channel means {num, e2, me} (AEWGS only)
- *   ws      : workspace, mhaq_fq_workspace_bytes(n_rows,n_inner) bytes;
- *             consumed by mhaq_fq_bwd_finalize_f32. */
+ *   ws      : workspace, consumed by mhaq_fq_bwd_finalize_f32. */
 int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx,
                     const float *scale, const float *zp, const float *lo, const float *hi,
                     int scale_stride, int zp_stride, int lo_stride, int hi_stride,
@@ -110,11 +116,13 @@ int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx,
                     const float *r, uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
                     const float *aewgs_stats, double *ws, void *stream);
 
-/* Deterministic second stage: per-channel sums in a fixed order, fp64.
+/* Deterministic second stage, one launch whatever the record count: per-channel sums in
+ * a fixed order in fp64 (slices of 1024 records in parallel, then a ticketed last-CTA sum
+ * of the slice sums in index order; no floating-point atomics, bitwise reproducible).
  * Each output is [n_ch] floats (or NULL to skip):
- *   g_scale = d/d scale,  g_zp = d/d zero_point,  g_lo = d/d min_val,
- *   g_hi = d/d max_val. */
-int mhaq_fq_bwd_finalize_f32(const double *ws, int64_t n_rows, int64_t n_inner, int64_t n_ch,
+ *   g_scale = d/d scale,  g_zp = d/d zero_point,  g_lo = d/d min_val,  g_hi = d/d max_val. */
+int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets,
+                             int64_t n_rows, int64_t n_inner, int64_t n_ch,
                              float *g_scale, float *g_zp, float *g_lo, float *g_hi,
                              void *stream);
 

@@ -30,32 +30,49 @@ constexpr int kSuperSubs = 4;              // sub-tiles per super-tile
 constexpr int kSuperElems = kSubElems * kSuperSubs;  // 16384
 constexpr int kU = 4;                      // independent 128-bit loads in flight per stream
 constexpr int kNPart = 8;                  // doubles per task record (MHAQ_FQ_NPART)
-constexpr int kMaxSpt = 64;
-constexpr int64_t kTargetTasks = 4096;
 
 struct Geom {
     int64_t n_rows, n_inner, n_ch;
-    int64_t subs_per_row;   // ceil(n_inner / 4096)
-    int64_t tasks_per_row;  // ceil(subs_per_row / spt)
-    int64_t n_tasks;        // n_rows * tasks_per_row
-    int spt;                // sub-tiles per task (1,2,4,...,64)
+    int64_t subs_per_row;    // ceil(n_inner / 4096)
+    int64_t tasks_per_row;   // ceil(subs_per_row / spt)
+    int64_t n_tasks;         // n_rows * tasks_per_row
+    int64_t groups_per_row;  // ceil(tasks_per_row / kGroupTasks): first level of the ticketed reduction
+    int64_t n_groups;        // n_rows * groups_per_row
+    int spt;                 // sub-tiles per task
 };
 
-// Pure function of the shape: host and device, forward/backward/finalize all
-// agree on it, which is what makes the workspace layout part of the ABI.
-__host__ __device__ inline Geom make_geom(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
+constexpr int kGroupTasks = 64;
+
+// Task-size policy.  Measured on B200 (profiles/r01_task_granularity.txt): with one CTA per
+// task and the hardware block scheduler balancing the SMs, SMALL tasks win — a lone CTA
+// sustains only ~16 GB/s, so big tasks leave a long under-subscribed tail.
+//   streaming kernels (forward, noise, stats): 1 sub-tile (4096 elements) per task
+//   backward: 2 sub-tiles per task when the tensor is big enough, halving the per-task
+//             flush (warp shuffles + ticket) cost per element
+enum { GEOM_STREAM = 0, GEOM_REDUCE = 1 };
+
+// Pure function of the shape (and policy): every kernel of a pass agrees on it, which is
+// what makes the workspace layout part of the ABI.
+__host__ __device__ inline Geom make_geom(int64_t n_rows, int64_t n_inner, int64_t n_ch, int policy,
+                                          int spt_override = 0) {
     Geom g;
     g.n_rows = n_rows;
     g.n_inner = n_inner;
     g.n_ch = n_ch < 1 ? 1 : n_ch;
     g.subs_per_row = (n_inner + kSubElems - 1) / kSubElems;
-    int64_t total = n_rows * g.subs_per_row;
+    const int64_t total = n_rows * g.subs_per_row;
     int spt = 1;
-    while (spt < kMaxSpt && (int64_t)spt * 2 <= g.subs_per_row && total / (spt * 2) >= kTargetTasks)
-        spt *= 2;
+    // 2 sub-tiles per task once that still leaves >= 4 waves of CTAs (148 SMs x 8 resident)
+    if (policy == GEOM_REDUCE && g.subs_per_row >= 2 && total >= 2 * 4736) spt = 2;
+    if (spt_override > 0) {
+        spt = spt_override;
+        while (spt > 1 && spt > g.subs_per_row) spt >>= 1;
+    }
     g.spt = spt;
     g.tasks_per_row = (g.subs_per_row + spt - 1) / spt;
     g.n_tasks = n_rows * g.tasks_per_row;
+    g.groups_per_row = (g.tasks_per_row + kGroupTasks - 1) / kGroupTasks;
+    g.n_groups = n_rows * g.groups_per_row;
     return g;
 }
 

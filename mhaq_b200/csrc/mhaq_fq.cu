@@ -12,6 +12,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo
 #include "fq_common.cuh"
 #include "../../include/mhaq_fq.h"
+#include <cstdlib>
 
 using namespace mhaq;
 
@@ -24,6 +25,11 @@ __device__ constexpr float kAewgsEps = 1e-3f;    // gdnsq.py:131
 __device__ constexpr float kAewgsCap = 0.99f;    // 1 - gap, gdnsq.py:136-139
 
 enum { NOISE_PHILOX = 0, NOISE_EXPLICIT = 1, NOISE_NONE = 2 };
+
+// resident CTAs per SM the backward kernel is compiled for (register cap = 65536/(128*N))
+#ifndef MHAQ_BWD_MIN_CTAS
+#define MHAQ_BWD_MIN_CTAS 7
+#endif
 
 // ===========================================================================
 // Forward
@@ -216,7 +222,6 @@ struct BwdConst {
     float smul;      // s (grad w.r.t. y) or 1 (grad w.r.t. codes)
     float rcp;       // RN(1/s) for the fast division sequences
     float delta;     // AEWGS per-channel delta
-    bool codegrad;
     bool lo_lt_hi, lo_gt_hi;
 };
 
@@ -237,7 +242,7 @@ __device__ __forceinline__ float estimator_gv(float g, float e, float delta) {
     }
 }
 
-template <int METHOD, bool CLAMP, int NOISE, bool FAST>
+template <int METHOD, bool CLAMP, int NOISE, bool FAST, bool CODEGRAD>
 __device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t sign_flip,
                                           const QConst &q, const BwdConst &bc, Acc &acc) {
     // ---- recompute the forward (gdnsq.py:197-208) ----
@@ -267,14 +272,15 @@ __device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t 
     const float code = f_add(v, e);
     // ---- gradient w.r.t. codes, then the estimator ----
     const float g = f_mul(go, bc.smul);                  // MulBackward of code*s
-    const float gv = estimator_gv<METHOD>(g, e, bc.delta);
-    float gu;                                            // DivBackward (self): gv / s
-    if (!FAST) {
-        gu = f_div(gv, q.s);
-    } else if ((METHOD == MHAQ_FQ_STE || METHOD == MHAQ_FQ_LSQ) && !bc.codegrad) {
-        gu = div_of_product(go, gv, q.s, bc.rcp);        // gv == RN(go*s) (or NaN)
+    float gv, gu;                                        // gu = DivBackward (self): gv / s
+    if (FAST && (METHOD == MHAQ_FQ_STE || METHOD == MHAQ_FQ_LSQ) && !CODEGRAD) {
+        // g + g*0 == g bit for bit unless g is inf (-> NaN); div_of_product maps an
+        // infinite g to NaN as well (inf*s - inf), so gx matches the reference either way
+        gv = g;
+        gu = div_of_product(go, gv, q.s, bc.rcp);        // gv == RN(go*s)
     } else {
-        gu = div_exact(gv, q.s, bc.rcp);
+        gv = estimator_gv<METHOD>(g, e, bc.delta);
+        gu = FAST ? div_exact(gv, q.s, bc.rcp) : f_div(gv, q.s);
     }
     const float gx = in ? gu : 0.f;                      // ClampBackward
     // ---- parameter-gradient partial sums ----
@@ -283,7 +289,7 @@ __device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t 
     // difference is all but exact) and only then accumulated: same terms as the
     // reference, summed without its catastrophic cancellation between two big fp32 sums.
     const float t2 = f_mul(gv, FAST ? div_exact(v, q.s, bc.rcp) : f_div(v, q.s));
-    if (!bc.codegrad) {
+    if (!CODEGRAD) {
         acc.se += f_sub(f_mul(go, code), t2);
         acc.sz += f_sub(go, gu);                         // (+zp of dequant) - (sub zp)
     } else {
@@ -306,15 +312,32 @@ __device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t 
     return gx;
 }
 
-// Exact input gradient for one element, true divisions (guard fall-back of the fast path).
+// Guard fall-back of the fast path (rare: tiny non-zero / huge gradients): recompute the
+// input gradient of one 16-element thread batch with true IEEE divisions, RE-LOADING the
+// operands (L2 hits) so that nothing of this path stays live in the streaming loop, and
+// overwrite what the fast path stored (same thread, program order).
 template <int METHOD, bool CLAMP>
-__device__ __noinline__ float gx_exact(float x, float go, QConst q, float smul, float delta) {
-    const float c = CLAMP ? f_clamp(x, q.lo, q.hi) : x;
-    const bool in = CLAMP ? ((x >= q.lo) && (x <= q.hi)) : (x == x);
-    const float v = f_div(f_sub(c, q.zp), q.s);
-    const float e = f_sub(rintf(v), v);
-    const float gv = estimator_gv<METHOD>(f_mul(go, smul), e, delta);
-    return in ? f_div(gv, q.s) : 0.f;
+__device__ __noinline__ void fix_batch_exact(const float *xr, const float *gr, float *gxr, int64_t p0,
+                                             QConst q, float smul, float delta) {
+#pragma unroll 1
+    for (int u = 0; u < kU; ++u) {
+        const int64_t p = p0 + u * kIterElems;
+        const float4 xv = *reinterpret_cast<const float4 *>(xr + p);
+        const float4 gv = *reinterpret_cast<const float4 *>(gr + p);
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float x = xs[i];
+            const float c = CLAMP ? f_clamp(x, q.lo, q.hi) : x;
+            const bool in = CLAMP ? ((x >= q.lo) && (x <= q.hi)) : (x == x);
+            const float v = f_div(f_sub(c, q.zp), q.s);
+            const float e = f_sub(rintf(v), v);
+            const float gvv = estimator_gv<METHOD>(f_mul(gs[i], smul), e, delta);
+            o[i] = in ? f_div(gvv, q.s) : 0.f;
+        }
+        *reinterpret_cast<float4 *>(gxr + p) = make_float4(o[0], o[1], o[2], o[3]);
+    }
 }
 
 // min over the 4 components of (bits<<1)-1: zero maps to 0xffffffff (never the minimum),
@@ -325,14 +348,128 @@ __device__ __forceinline__ uint32_t nzmin4(uint32_t m, const float4 &v) {
     return min(min(min(m, a), min(b, c)), d);
 }
 
-template <int METHOD, bool CLAMP, int NOISE, bool VEC>
-__global__ void __launch_bounds__(kThreads)
+// Per-task epilogue of the backward kernel: fp32 partials -> warp shuffle -> fp64 sum over
+// the 4 warps -> one record per task.  No fences, no atomics: the kernel boundary orders the
+// records before the finalize kernel, so the streaming kernel's CTAs retire immediately.
+template <bool CLAMP>
+__device__ __forceinline__ void flush_record(const Acc &acc, int64_t t, double *__restrict__ ws) {
+    __shared__ float s_red[5][kThreads / 32];
+    const int tid = threadIdx.x;
+    float v0 = warp_sum(acc.se), v1 = warp_sum(acc.sn), v2 = warp_sum(acc.sz);
+    float v3 = CLAMP ? warp_sum(acc.sl) : 0.f, v4 = CLAMP ? warp_sum(acc.sh) : 0.f;
+    if ((tid & 31) == 0) {
+        const int w = tid >> 5;
+        s_red[0][w] = v0; s_red[1][w] = v1; s_red[2][w] = v2; s_red[3][w] = v3; s_red[4][w] = v4;
+    }
+    __syncthreads();
+    if (tid < 5) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) a += (double)s_red[tid][w];
+        ws[t * kNPart + tid] = a;
+    }
+    __syncthreads();
+}
+
+// Deterministic second stage, ONE launch for any record count.
+// grid = (slices, n_ch).  CTA (sl, ch) sums records [sl*kSliceRecs, ...) of channel ch in a
+// fixed order (thread-strided, then a fixed tree) -> slice record.  The last CTA of a channel
+// to finish (ticket) sums the channel's slice records in index order and writes the
+// gradients.  Which CTA performs the last step varies run to run; the summation order, hence
+// the result, does not.  Tickets are zero on entry and restored to zero.
+constexpr int kSliceRecs = 1024;
+constexpr int kFinThreads = 256;
+
+template <int NCOL>
+__device__ __forceinline__ void block_sum_cols(double (&a)[NCOL], double (*s)[kFinThreads]) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int m = 0; m < NCOL; ++m) s[m][tid] = a[m];
+    __syncthreads();
+    for (int o = kFinThreads / 2; o > 0; o >>= 1) {
+        if (tid < o) {
+#pragma unroll
+            for (int m = 0; m < NCOL; ++m) s[m][tid] += s[m][tid + o];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < NCOL; ++m) a[m] = s[m][0];
+    __syncthreads();
+}
+
+// record index of the i-th record of channel ch (rows r = ch + k*n_ch, tasks_per_row each)
+__device__ __forceinline__ int64_t chan_record(const Geom &g, int64_t ch, int64_t i) {
+    const int64_t rr = i / g.tasks_per_row;
+    return (rr * g.n_ch + ch) * g.tasks_per_row + (i - rr * g.tasks_per_row);
+}
+
+template <int NCOL, typename Emit>
+__device__ __forceinline__ void finalize_channel(const double *ws, double *slice_ws,
+                                                 unsigned int *tickets, const Geom &g, Emit emit) {
+    __shared__ double s[NCOL][kFinThreads];
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const int64_t ch = blockIdx.y, sl = blockIdx.x, n_sl = gridDim.x;
+    const int64_t recs = (g.n_rows / g.n_ch) * g.tasks_per_row;
+    const int64_t i0 = sl * kSliceRecs;
+    const int64_t i1 = (i0 + kSliceRecs < recs) ? i0 + kSliceRecs : recs;
+    double a[NCOL];
+#pragma unroll
+    for (int m = 0; m < NCOL; ++m) a[m] = 0.0;
+    for (int64_t i = i0 + tid; i < i1; i += kFinThreads) {
+        const double *rec = ws + chan_record(g, ch, i) * kNPart;
+#pragma unroll
+        for (int m = 0; m < NCOL; ++m) a[m] += rec[m];
+    }
+    block_sum_cols<NCOL>(a, s);
+    if (n_sl == 1) {
+        if (tid == 0) emit(ch, a);
+        return;
+    }
+    if (tid == 0) {
+        double *o = slice_ws + (ch * n_sl + sl) * kNPart;
+#pragma unroll
+        for (int m = 0; m < NCOL; ++m) o[m] = a[m];
+        __threadfence();
+        s_last = (atomicAdd(&tickets[ch], 1u) == (unsigned)(n_sl - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+#pragma unroll
+    for (int m = 0; m < NCOL; ++m) a[m] = 0.0;
+    for (int64_t i = tid; i < n_sl; i += kFinThreads) {
+        const double *o = slice_ws + (ch * n_sl + i) * kNPart;
+#pragma unroll
+        for (int m = 0; m < NCOL; ++m) a[m] += __ldcg(o + m);
+    }
+    block_sum_cols<NCOL>(a, s);
+    if (tid == 0) {
+        emit(ch, a);
+        tickets[ch] = 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kFinThreads)
+fq_bwd_finalize_kernel(const double *__restrict__ ws, double *slice_ws, unsigned int *tickets,
+                       Geom g, float *__restrict__ g_scale, float *__restrict__ g_zp,
+                       float *__restrict__ g_lo, float *__restrict__ g_hi) {
+    finalize_channel<5>(ws, slice_ws, tickets, g, [=](int64_t ch, const double (&a)[5]) {
+        if (g_scale) g_scale[ch] = (float)(a[0] + a[1]);
+        if (g_zp) g_zp[ch] = (float)a[2];
+        if (g_lo) g_lo[ch] = (float)a[3];
+        if (g_hi) g_hi[ch] = (float)a[4];
+    });
+}
+
+template <int METHOD, bool CLAMP, int NOISE, bool VEC, bool CODEGRAD>
+__global__ void __launch_bounds__(kThreads, MHAQ_BWD_MIN_CTAS)
 fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *__restrict__ gx,
-              QParams prm, Geom g, int codegrad, const float *__restrict__ r, uint64_t seed,
+              QParams prm, Geom g, const float *__restrict__ r, uint64_t seed,
               uint64_t offset, const uint64_t *__restrict__ philox_dev,
               const float *__restrict__ aewgs_stats, double *__restrict__ ws) {
     const int tid = threadIdx.x;
-    __shared__ float s_red[5][kThreads / 32];
     PhiloxKey key = {0, 0, 0, 0};
     if (NOISE == NOISE_PHILOX) key = make_key(seed, offset, philox_dev);
     const int64_t supers_per_row = (g.n_inner + kSuperElems - 1) / kSuperElems;
@@ -342,8 +479,7 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
         const Task k = make_task(g, t);
         const QConst q = load_qconst(prm, k.ch);
         BwdConst bc;
-        bc.codegrad = codegrad != 0;
-        bc.smul = bc.codegrad ? 1.f : q.s;
+        bc.smul = CODEGRAD ? 1.f : q.s;
         bc.rcp = __frcp_rn(q.s);
         bc.lo_lt_hi = q.lo < q.hi;
         bc.lo_gt_hi = q.lo > q.hi;
@@ -378,6 +514,12 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
             }
             if (fast_ok && full) {
                 // ---------------- fast path: full, aligned sub-tile ----------------
+                // one Philox word (32 bits) covers the 8 iterations x 4 elements of a sub-tile
+                uint32_t nw = 0;
+                if (NOISE == NOISE_PHILOX) {
+                    const int wi = (int)(sub & (kSuperSubs - 1));
+                    nw = ~((wi < 2) ? ((wi == 0) ? rnd.x : rnd.y) : ((wi == 2) ? rnd.z : rnd.w));
+                }
 #pragma unroll
                 for (int b = 0; b < kSubIters / kU; ++b) {
                     float4 xv[kU], gv[kU], rv4[kU];
@@ -396,27 +538,24 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
 #pragma unroll
                     for (int u = 0; u < kU; ++u) {
                         mn = nzmin4(mn, gv[u]);
-                        if (!kProductDiv || bc.codegrad) mx = absmax4(mx, gv[u]);
+                        if (!kProductDiv || CODEGRAD) mx = absmax4(mx, gv[u]);
                     }
                     const bool odd = (mn < kGoLoBits2m1) || (mx > kGvHi);
 #pragma unroll
                     for (int u = 0; u < kU; ++u) {
                         const int64_t p = base + (b * kU + u) * kIterElems;
-                        uint32_t inv = 0;
-                        if (NOISE == NOISE_PHILOX) inv = ~noise_nibble(rnd, it0 + b * kU + u);
+                        constexpr int kTop = 31;
+                        const int sh = (b * kU + u) * 4;     // compile-time after unrolling
                         float4 o;
-                        o.x = bwd_elem<METHOD, CLAMP, NOISE, true>(xv[u].x, gv[u].x, rv4[u].x, inv << 31, q, bc, acc);
-                        o.y = bwd_elem<METHOD, CLAMP, NOISE, true>(xv[u].y, gv[u].y, rv4[u].y, inv << 30, q, bc, acc);
-                        o.z = bwd_elem<METHOD, CLAMP, NOISE, true>(xv[u].z, gv[u].z, rv4[u].z, inv << 29, q, bc, acc);
-                        o.w = bwd_elem<METHOD, CLAMP, NOISE, true>(xv[u].w, gv[u].w, rv4[u].w, inv << 28, q, bc, acc);
-                        if (odd) {   // rare: tiny / huge gradients -> exact IEEE division for gx
-                            o.x = gx_exact<METHOD, CLAMP>(xv[u].x, gv[u].x, q, bc.smul, bc.delta);
-                            o.y = gx_exact<METHOD, CLAMP>(xv[u].y, gv[u].y, q, bc.smul, bc.delta);
-                            o.z = gx_exact<METHOD, CLAMP>(xv[u].z, gv[u].z, q, bc.smul, bc.delta);
-                            o.w = gx_exact<METHOD, CLAMP>(xv[u].w, gv[u].w, q, bc.smul, bc.delta);
-                        }
+                        o.x = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].x, gv[u].x, rv4[u].x, nw << (kTop - sh - 0), q, bc, acc);
+                        o.y = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].y, gv[u].y, rv4[u].y, nw << (kTop - sh - 1), q, bc, acc);
+                        o.z = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].z, gv[u].z, rv4[u].z, nw << (kTop - sh - 2), q, bc, acc);
+                        o.w = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].w, gv[u].w, rv4[u].w, nw << (kTop - sh - 3), q, bc, acc);
                         if (gxr) st_stream4(gxr + p, o);
                     }
+                    if (odd && gxr)   // rare: exact IEEE division for the input gradient
+                        fix_batch_exact<METHOD, CLAMP>(xr, gr, gxr, base + (b * kU) * kIterElems, q,
+                                                       bc.smul, bc.delta);
                 }
                 continue;
             }
@@ -442,64 +581,15 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
                     uint32_t inv = 0;
                     if (NOISE == NOISE_PHILOX) inv = ~noise_nibble(rnd, it0 + b * kU + u);
                     float4 o;
-                    o.x = bwd_elem<METHOD, CLAMP, NOISE, false>(xv[u].x, gv[u].x, rv4[u].x, inv << 31, q, bc, acc);
-                    o.y = bwd_elem<METHOD, CLAMP, NOISE, false>(xv[u].y, gv[u].y, rv4[u].y, inv << 30, q, bc, acc);
-                    o.z = bwd_elem<METHOD, CLAMP, NOISE, false>(xv[u].z, gv[u].z, rv4[u].z, inv << 29, q, bc, acc);
-                    o.w = bwd_elem<METHOD, CLAMP, NOISE, false>(xv[u].w, gv[u].w, rv4[u].w, inv << 28, q, bc, acc);
+                    o.x = bwd_elem<METHOD, CLAMP, NOISE, false, CODEGRAD>(xv[u].x, gv[u].x, rv4[u].x, inv << 31, q, bc, acc);
+                    o.y = bwd_elem<METHOD, CLAMP, NOISE, false, CODEGRAD>(xv[u].y, gv[u].y, rv4[u].y, inv << 30, q, bc, acc);
+                    o.z = bwd_elem<METHOD, CLAMP, NOISE, false, CODEGRAD>(xv[u].z, gv[u].z, rv4[u].z, inv << 29, q, bc, acc);
+                    o.w = bwd_elem<METHOD, CLAMP, NOISE, false, CODEGRAD>(xv[u].w, gv[u].w, rv4[u].w, inv << 28, q, bc, acc);
                     if (gxr) store4<VEC>(gxr, p, g.n_inner, o);
                 }
             }
         }
-        // ---- flush one record per task: fp32 within a warp, fp64 across warps ----
-        float v0 = warp_sum(acc.se), v1 = warp_sum(acc.sn), v2 = warp_sum(acc.sz);
-        float v3 = CLAMP ? warp_sum(acc.sl) : 0.f, v4 = CLAMP ? warp_sum(acc.sh) : 0.f;
-        if ((tid & 31) == 0) {
-            const int w = tid >> 5;
-            s_red[0][w] = v0; s_red[1][w] = v1; s_red[2][w] = v2; s_red[3][w] = v3; s_red[4][w] = v4;
-        }
-        __syncthreads();
-        if (tid < 5) {
-            double a = 0.0;
-#pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) a += (double)s_red[tid][w];
-            ws[t * kNPart + tid] = a;
-        }
-        __syncthreads();
-    }
-}
-
-// One CTA per channel; fixed-order fp64 sums over the records of that channel.
-__global__ void __launch_bounds__(256)
-fq_bwd_finalize_kernel(const double *__restrict__ ws, Geom g, float *__restrict__ g_scale,
-                       float *__restrict__ g_zp, float *__restrict__ g_lo, float *__restrict__ g_hi) {
-    __shared__ double s[5][256];
-    const int64_t ch = blockIdx.x;
-    const int64_t rows_per_ch = g.n_rows / g.n_ch;
-    const int64_t recs = rows_per_ch * g.tasks_per_row;
-    double a[5] = {0, 0, 0, 0, 0};
-    for (int64_t i = threadIdx.x; i < recs; i += 256) {
-        const int64_t rr = i / g.tasks_per_row;
-        const int64_t j = i - rr * g.tasks_per_row;
-        const int64_t t = (rr * g.n_ch + ch) * g.tasks_per_row + j;
-        const double *rec = ws + t * kNPart;
-#pragma unroll
-        for (int m = 0; m < 5; ++m) a[m] += rec[m];
-    }
-#pragma unroll
-    for (int m = 0; m < 5; ++m) s[m][threadIdx.x] = a[m];
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) {
-#pragma unroll
-            for (int m = 0; m < 5; ++m) s[m][threadIdx.x] += s[m][threadIdx.x + o];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        if (g_scale) g_scale[ch] = (float)(s[0][0] + s[1][0]);
-        if (g_zp) g_zp[ch] = (float)s[2][0];
-        if (g_lo) g_lo[ch] = (float)s[3][0];
-        if (g_hi) g_hi[ch] = (float)s[4][0];
+        flush_record<CLAMP>(acc, t, ws);
     }
 }
 
@@ -727,6 +817,21 @@ inline int grid_for(int64_t n_tasks) {
     return (int)(n_tasks < cap ? n_tasks : cap);
 }
 
+// experiment knob (not part of the ABI): MHAQ_FQ_BWD_SPT / MHAQ_FQ_FWD_SPT force the
+// sub-tiles-per-task of the reducing / streaming kernels (power of two).
+inline int env_int(const char *name) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+inline Geom stream_geom(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
+    static const int ov = env_int("MHAQ_FQ_FWD_SPT");
+    return make_geom(n_rows, n_inner, n_ch, GEOM_STREAM, ov);
+}
+inline Geom reduce_geom(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
+    static const int ov = env_int("MHAQ_FQ_BWD_SPT");
+    return make_geom(n_rows, n_inner, n_ch, GEOM_REDUCE, ov);
+}
+
 inline int last_error() {
     cudaError_t e = cudaGetLastError();
     return (int)e;
@@ -736,12 +841,14 @@ template <int METHOD, bool CLAMP, int NOISE>
 int launch_bwd(bool vec, int grid, cudaStream_t st, const float *go, const float *x, float *gx,
                const QParams &prm, const Geom &g, int codegrad, const float *r, uint64_t seed,
                uint64_t offset, const uint64_t *philox_dev, const float *stats, double *ws) {
-    if (vec)
-        fq_bwd_kernel<METHOD, CLAMP, NOISE, true><<<grid, kThreads, 0, st>>>(
-            go, x, gx, prm, g, codegrad, r, seed, offset, philox_dev, stats, ws);
-    else
-        fq_bwd_kernel<METHOD, CLAMP, NOISE, false><<<grid, kThreads, 0, st>>>(
-            go, x, gx, prm, g, codegrad, r, seed, offset, philox_dev, stats, ws);
+#define MHAQ_LAUNCH(V, C)                                                             \
+    fq_bwd_kernel<METHOD, CLAMP, NOISE, V, C><<<grid, kThreads, 0, st>>>(             \
+        go, x, gx, prm, g, r, seed, offset, philox_dev, stats, ws)
+    if (vec && !codegrad) MHAQ_LAUNCH(true, false);
+    else if (vec) MHAQ_LAUNCH(true, true);
+    else if (!codegrad) MHAQ_LAUNCH(false, false);
+    else MHAQ_LAUNCH(false, true);
+#undef MHAQ_LAUNCH
     return last_error();
 }
 
@@ -775,13 +882,26 @@ const char *mhaq_fq_build_info(void) {
 
 int64_t mhaq_fq_num_tasks(int64_t n_rows, int64_t n_inner) {
     if (n_rows <= 0 || n_inner <= 0) return 0;
-    return make_geom(n_rows, n_inner, 1).n_tasks;
+    return stream_geom(n_rows, n_inner, 1).n_tasks;   // the finest decomposition any kernel uses
+}
+
+static inline int64_t n_slices_of(const Geom &g) {
+    const int64_t recs = (g.n_rows / g.n_ch) * g.tasks_per_row;
+    return (recs + kSliceRecs - 1) / kSliceRecs;
 }
 
 int64_t mhaq_fq_workspace_bytes(int64_t n_rows, int64_t n_inner) {
-    int64_t t = mhaq_fq_num_tasks(n_rows, n_inner);
-    if (t < 1) t = 1;
-    return t * kNPart * (int64_t)sizeof(double);
+    if (n_rows <= 0 || n_inner <= 0) return kNPart * (int64_t)sizeof(double);
+    const Geom gs = stream_geom(n_rows, n_inner, 1), gr = reduce_geom(n_rows, n_inner, 1);
+    const int64_t tasks = gs.n_tasks > gr.n_tasks ? gs.n_tasks : gr.n_tasks;
+    // records + slice records (at most one slice record per kSliceRecs records, >= 1 per row)
+    const int64_t slices = tasks / kSliceRecs + n_rows + 1;
+    return (tasks + slices) * kNPart * (int64_t)sizeof(double);
+}
+
+int64_t mhaq_fq_ticket_count(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
+    (void)n_rows; (void)n_inner;
+    return n_ch > 0 ? n_ch : 1;
 }
 
 int mhaq_fq_fwd_f32(const float *x, float *y, float *codes, const float *scale, const float *zp,
@@ -794,7 +914,7 @@ int mhaq_fq_fwd_f32(const float *x, float *y, float *codes, const float *scale, 
         !stride_ok(hi_stride))
         return MHAQ_FQ_EINVAL;
     if (n_rows == 0 || n_inner == 0) return 0;
-    const Geom g = make_geom(n_rows, n_inner, n_ch);
+    const Geom g = stream_geom(n_rows, n_inner, n_ch);
     const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride};
     const bool vec = (n_inner % 4 == 0) && aligned16(x) && (!y || aligned16(y)) &&
                      (!codes || aligned16(codes));
@@ -834,7 +954,7 @@ int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx, const float *sca
     if (method < 0 || method > 3) return MHAQ_FQ_EINVAL;
     if (method == MHAQ_FQ_AEWGS && !aewgs_stats) return MHAQ_FQ_ENULL;
     if (n_rows == 0 || n_inner == 0) return 0;
-    const Geom g = make_geom(n_rows, n_inner, n_ch);
+    const Geom g = reduce_geom(n_rows, n_inner, n_ch);
     const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride};
     const bool vec = (n_inner % 4 == 0) && aligned16(x) && aligned16(go) &&
                      (!gx || aligned16(gx)) && (!r || aligned16(r));
@@ -856,13 +976,18 @@ int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx, const float *sca
 #undef MHAQ_BWD
 }
 
-int mhaq_fq_bwd_finalize_f32(const double *ws, int64_t n_rows, int64_t n_inner, int64_t n_ch,
-                             float *g_scale, float *g_zp, float *g_lo, float *g_hi, void *stream) {
-    if (!ws) return MHAQ_FQ_ENULL;
+int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets, int64_t n_rows, int64_t n_inner,
+                             int64_t n_ch, float *g_scale, float *g_zp, float *g_lo, float *g_hi,
+                             void *stream) {
+    if (!ws || !tickets) return MHAQ_FQ_ENULL;
     if (n_rows <= 0 || n_inner <= 0 || n_ch < 1 || (n_rows % n_ch) != 0) return MHAQ_FQ_EINVAL;
-    const Geom g = make_geom(n_rows, n_inner, n_ch);
-    fq_bwd_finalize_kernel<<<(int)n_ch, 256, 0, (cudaStream_t)stream>>>(ws, g, g_scale, g_zp, g_lo,
-                                                                       g_hi);
+    const Geom g = reduce_geom(n_rows, n_inner, n_ch);
+    const int64_t n_sl = n_slices_of(g);
+    if (n_sl > 65535 * 32 || n_ch > 65535) return MHAQ_FQ_EINVAL;
+    dim3 grid((unsigned)n_sl, (unsigned)n_ch);
+    double *slice_ws = ws + g.n_tasks * kNPart;
+    fq_bwd_finalize_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(ws, slice_ws, tickets, g,
+                                                                        g_scale, g_zp, g_lo, g_hi);
     return last_error();
 }
 
@@ -874,7 +999,7 @@ int mhaq_fq_aewgs_stats_f32(const float *go, const float *x, const float *scale,
     if (rc) return rc;
     if (!go || !ws) return MHAQ_FQ_ENULL;
     if (n_rows == 0 || n_inner == 0) return 0;
-    const Geom g = make_geom(n_rows, n_inner, n_ch);
+    const Geom g = stream_geom(n_rows, n_inner, n_ch);
     const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride};
     const bool vec = (n_inner % 4 == 0) && aligned16(x) && aligned16(go);
     const int grid = grid_for(g.n_tasks);
@@ -890,7 +1015,7 @@ int mhaq_fq_aewgs_stats_finalize_f32(const double *ws, int64_t n_rows, int64_t n
                                      int64_t n_ch, float *stats, void *stream) {
     if (!ws || !stats) return MHAQ_FQ_ENULL;
     if (n_rows <= 0 || n_inner <= 0 || n_ch < 1 || (n_rows % n_ch) != 0) return MHAQ_FQ_EINVAL;
-    const Geom g = make_geom(n_rows, n_inner, n_ch);
+    const Geom g = stream_geom(n_rows, n_inner, n_ch);
     fq_aewgs_stats_finalize_kernel<<<(int)n_ch, 256, 0, (cudaStream_t)stream>>>(ws, g, stats);
     return last_error();
 }
@@ -926,7 +1051,7 @@ int mhaq_fq_noise_f32(float *r, int64_t n_rows, int64_t n_inner, uint64_t seed, 
     if (!r) return MHAQ_FQ_ENULL;
     if (n_rows < 0 || n_inner < 0) return MHAQ_FQ_EINVAL;
     if (n_rows == 0 || n_inner == 0) return 0;
-    const Geom g = make_geom(n_rows, n_inner, 1);
+    const Geom g = stream_geom(n_rows, n_inner, 1);
     fq_noise_kernel<<<grid_for(g.n_tasks), kThreads, 0, (cudaStream_t)stream>>>(r, g, seed, offset,
                                                                                philox_dev);
     return last_error();

@@ -124,6 +124,23 @@ def _workspace(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
     return torch.empty(nbytes // 8, dtype=torch.float64, device=x.device)
 
 
+# Ticket counters of the deterministic finalize kernel: zero on entry, restored to zero by
+# the kernel, so ONE zero-initialised buffer per (device, stream) is reused by every call
+# ordered on that stream (include/mhaq_fq.h).
+_ticket_bufs = {}
+
+
+def _tickets(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
+    need = lib.mhaq_fq_ticket_count(geo.n_rows, geo.n_inner, geo.n_ch)
+    key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+    buf = _ticket_bufs.get(key)
+    if buf is None or buf.numel() < need:
+        n = max(4096, 1 << (int(need) - 1).bit_length())
+        buf = torch.zeros(n, dtype=torch.int32, device=x.device)
+        _ticket_bufs[key] = buf
+    return buf
+
+
 def _next_philox(device: torch.device) -> Tuple[int, int]:
     """Draw a fresh (seed, offset) pair from torch's CUDA generator of `device`."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -218,9 +235,9 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
     go = go.contiguous()
     gx = torch.empty_like(x) if need_gx else None
     n_ch = geo.n_ch
-    out = torch.zeros(4, n_ch, dtype=torch.float32, device=x.device)
     if x.numel() == 0:
-        return gx, out
+        return gx, torch.zeros(4, n_ch, dtype=torch.float32, device=x.device)
+    out = torch.empty(4, n_ch, dtype=torch.float32, device=x.device)   # fully written by the kernel
     if method == METHOD_IDS["AEWGS"] and geo.axis is None:
         raise NotImplementedError(
             "per-tensor AEWGS reduces its statistics over dim 0 only in the reference "
@@ -243,11 +260,12 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
                 pdev = pd
             else:
                 seed, offset = _next_philox(x.device)
+    tk = _tickets(x, geo)
     check(lib.mhaq_fq_bwd_f32(_ptr(go), _ptr(x), _ptr(gx), *L.params(),
                               geo.n_rows, geo.n_inner, geo.n_ch, method, int(code_grad),
                               _ptr(noise), seed, offset, _ptr(pdev), _ptr(stats), _ptr(ws), _stream()),
           "mhaq_fq_bwd_f32")
-    check(lib.mhaq_fq_bwd_finalize_f32(_ptr(ws), geo.n_rows, geo.n_inner, geo.n_ch,
+    check(lib.mhaq_fq_bwd_finalize_f32(_ptr(ws), _ptr(tk), geo.n_rows, geo.n_inner, geo.n_ch,
                                        _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]),
                                        _stream()),
           "mhaq_fq_bwd_finalize_f32")

@@ -27,7 +27,7 @@ def test_header_symbols_all_exported():
 
 def test_abi_version_and_info():
     from mhaq_b200 import _lib
-    assert _lib.lib.mhaq_fq_abi_version() == 1
+    assert _lib.lib.mhaq_fq_abi_version() == 2
     assert b"sm_100a" in _lib.lib.mhaq_fq_build_info()
 
 
@@ -39,12 +39,12 @@ def test_geometry_is_a_pure_function_of_shape():
     assert L.mhaq_fq_num_tasks(512, 4608) == 1024
     assert L.mhaq_fq_num_tasks(64, 576) == 64
     assert L.mhaq_fq_num_tasks(0, 10) == 0
-    # large tensors are cut into >= 4096 tasks of up to 64 sub-tiles
-    assert L.mhaq_fq_num_tasks(1, 1 << 30) == 4096
-    assert L.mhaq_fq_workspace_bytes(1, 1 << 30) == 4096 * 8 * 8
-    n = 256 * 64 * 56 * 56
-    t = L.mhaq_fq_num_tasks(1, n)
-    assert 4096 <= t <= 8192 + 1
+    # streaming kernels: one task per 4096-element sub-tile
+    assert L.mhaq_fq_num_tasks(1, 1 << 30) == 1 << 18
+    # one finalize ticket per channel
+    assert L.mhaq_fq_ticket_count(1, 1 << 30, 1) == 1
+    assert L.mhaq_fq_ticket_count(512, 4608, 512) == 512
+    assert L.mhaq_fq_workspace_bytes(1, 1 << 30) >= (1 << 18) * 8 * 8
 
 
 def test_argument_errors_without_gpu():
@@ -60,6 +60,8 @@ def test_argument_errors_without_gpu():
     # bad method
     assert L.mhaq_fq_bwd_f32(dummy, dummy, dummy, dummy, dummy, None, None, 0, 0, 0, 0, 1, 8, 1, 9, 0,
                              None, 0, 0, None, None, dummy, None) == -1
+    # missing tickets buffer
+    assert L.mhaq_fq_bwd_finalize_f32(dummy, None, 1, 8, 1, None, None, None, None, None) == -2
     with pytest.raises(RuntimeError, match="EINVAL"):
         _lib.check(-1, "x")
 
