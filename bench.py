@@ -47,6 +47,11 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also run the config-2 sweep -> gpurun_out/")
     ap.add_argument("--cpu-log2n", type=int, default=24)
+    ap.add_argument("--no-resnet", action="store_true", help="skip the ResNet-18 W4A4 QAT leg")
+    ap.add_argument("--resnet-batch", type=int, default=256, help="per-GPU batch (config 4)")
+    ap.add_argument("--resnet-steps", type=int, default=12)
+    ap.add_argument("--no-eager-ref", action="store_true",
+                    help="skip timing the reference's ATen chain on the GPU (second denominator)")
     return ap.parse_args()
 
 
@@ -166,6 +171,103 @@ def time_region(fn, steps, sync_dist):
 
 
 # ---------------------------------------------------------------------------
+def resnet18_leg(a, dev, world, rank, use_dist):
+    """BASELINE configs[3]: torchvision ResNet-18, ImageNet-shaped synthetic batch (256 per GPU,
+    224x224), GDNSQ/STE W4A4 per-channel, distillation (Symmetrical KL) from a frozen FP copy,
+    RAdam lr 3e-4, fp32 + TF32 convolutions, DDP over NCCL for N > 1 — through
+    Quantizer(config)().quantize(lmodel) and the patched training_step."""
+    from mhaq_b200 import harness
+    torch.backends.cudnn.benchmark = True
+    torch.set_float32_matmul_precision("high")
+    B = a.resnet_batch
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(B, 3, 224, 224, device=dev, generator=g)
+    t = torch.randint(0, 1000, (B,), device=dev, generator=g)
+    q = harness.build_qat("resnet18", dev, qnmethod="STE", act_bit=4, weight_bit=4, distillation=True,
+                          calib_batch=x[: min(B, 64)])
+    if use_dist:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        q.model = DDP(q.model, device_ids=[dev.index], find_unused_parameters=True,
+                      gradient_as_bucket_view=True)
+    opt = q.configure_optimizers()
+    q.train(); q.wrapped_criterion.train(); q.tmodel.eval()
+    hx = x.cpu().pin_memory(); ht = t.cpu().pin_memory()
+    hloss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step():
+        loss = q.training_step((x, t), 0)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss
+
+    def step_e2e():
+        xd = hx.to(dev, non_blocking=True); td = ht.to(dev, non_blocking=True)
+        loss = q.training_step((xd, td), 0)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        hloss.copy_(loss.detach(), non_blocking=True)
+
+    for _ in range(4):
+        step()
+    k = a.resnet_steps
+    ms = time_region(step, k, use_dist) / k
+    ms_e = time_region(step_e2e, max(3, k // 2), use_dist) / max(3, k // 2)
+    res = {"workload": "configs[3] ResNet-18 224x224 STE W4A4 QAT, distillation, RAdam, fp32/TF32, "
+                       f"batch {B}/GPU, {'DDP dp%d' % world if use_dist else 'single GPU'}",
+           "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
+           "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1), "n_gpus": world,
+           "quantized_act_elems_per_step": 1680896 * B}
+    if rank == 0:
+        try:   # share of the step spent in the fake-quant kernels (CUPTI kernel times)
+            from torch.profiler import profile, ProfilerActivity
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step(); step()
+                torch.cuda.synchronize()
+            tot = fq = 0.0
+            for ev in prof.key_averages():
+                dt = getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0)
+                tot += dt
+                if "fq_" in ev.key:
+                    fq += dt
+            if tot > 0:
+                res["fake_quant_kernel_share"] = round(fq / tot, 4)
+                res["fake_quant_ms_per_step"] = round(fq / 2 / 1e3, 3)
+        except Exception as exc:   # profiler unavailable: the throughput numbers stand alone
+            res["fake_quant_kernel_share"] = None
+            res["profiler_error"] = str(exc)[:80]
+    del q, opt
+    torch.cuda.empty_cache()
+    return res
+
+
+def eager_reference_leg(a, dev):
+    """The reference's own ATen chain (the oracle port, same ops) executed eagerly on the B200:
+    the honest speed-up denominator for the fused kernels."""
+    from oracle import fq_oracle as O
+    b = argparse.Namespace(**vars(a))
+    b.log2n = min(a.log2n, 26)
+    n = 1 << b.log2n
+    x, go, scale, zp, lo, hi = make_inputs(b, dev)
+    lo_ = -math.inf if lo is None else lo
+    hi_ = math.inf if hi is None else hi
+    sp = scale.clone().requires_grad_(True)
+
+    def step():
+        xs = x.detach().requires_grad_(True)
+        sp.grad = None
+        y = O.fake_quant(xs, sp, zp, lo_, hi_, method=a.method)
+        y.backward(go)
+
+    for _ in range(3):
+        step()
+    ms = time_region(step, 10, False) / 10
+    return {"value": round(20 * n / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "ms_per_step": round(ms, 3),
+            "what": f"reference ATen op chain (oracle port) run eagerly on this GPU, N=2^{b.log2n}"}
+
+
+# ---------------------------------------------------------------------------
 def run_ours(a):
     import mhaq_b200
     from mhaq_b200 import ops
@@ -282,7 +384,15 @@ def run_ours(a):
                           "api": "mhaq_b200.fake_quant(...).backward() with pinned host x/go in, y/gx/g_scale out"}
         del hx, hg, hy, hgx, dx, dg
 
+    del x, go
+    torch.cuda.empty_cache()
+    if not a.no_resnet:
+        rn = resnet18_leg(a, dev, world, rank, use_dist)
+        if rank == 0:
+            out["resnet18_w4a4_qat"] = rn
     if rank == 0:
+        if not a.no_eager_ref:
+            out["reference_eager_gpu"] = eager_reference_leg(a, dev)
         if not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, steps=5, warmup=2)
         if a.sweep:

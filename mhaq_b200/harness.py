@@ -1,0 +1,228 @@
+"""Minimal stand-in for the Lightning side of the reference, used by the benchmarks and tests.
+
+Lightning, torchmetrics and pytorchcv are absent from this image (and the GPU box has no
+network), so ``Trainer.fit`` cannot run here.  This module mirrors only what the hot path
+needs from it, in the same order Lightning executes it:
+
+* ``LModule``  — the attributes/methods ``GDNSQQuant.quantize`` touches on a
+  ``LVisionCls`` (reference src/models/compose/vision/vision_cls_module.py:10-93);
+* ``make_config`` — the ``config.quantization`` tree of the YAML configs;
+* ``calibrate`` — the effect of ``Trainer.calibrate`` (training/trainer.py:187-223,
+  calib/minmaxobserver.py:39-88) from one batch;
+* ``fit_steps`` — forward → loss → backward → optimizer step, optionally under
+  ``DistributedDataParallel`` (one process per GPU, NCCL), the strategy the reference's
+  ``Trainer`` picks (training/trainer.py:92-97).
+
+With Lightning installed the real ``Trainer.fit`` drives the same quantized module.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Callable, Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .quantization.gdnsq.layers.gdnsq_act import NoisyAct
+from .quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
+from .quantization.gdnsq.layers.gdnsq_linear import NoisyLinear
+
+
+class LModule(nn.Module):
+    """Duck-typed LightningModule: model + criterion + optimizer factory + log sink."""
+
+    def __init__(self, model: nn.Module, criterion: Callable, optimizer=torch.optim.RAdam,
+                 lr: float = 3e-4):
+        super().__init__()
+        self.model = model
+        self.criterion = criterion
+        self.optimizer = optimizer
+        self.lr = lr
+        self.metrics: List = []
+        self.logged: Dict[str, object] = {}
+        self.trainer = SimpleNamespace(logged_metrics={})
+
+    # Lightning's self.log(..., sync_dist=True) all-reduces one scalar per call; here the
+    # values are kept on the device and never synchronised inside the step.
+    def log(self, name, value, **kw):
+        self.logged[name] = value.detach() if torch.is_tensor(value) else value
+
+    def configure_optimizers(self):
+        return self.optimizer([p for p in self.parameters() if p.requires_grad], self.lr)
+
+    def forward(self, inputs):
+        return self.model(inputs)
+
+    def training_step(self, batch, batch_idx):
+        inputs, target = batch
+        loss = self.criterion(self.model(inputs), target)
+        self.log("loss", loss)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        inputs, target = batch
+        return self.criterion(self.forward(inputs), target)
+
+    def test_step(self, batch, batch_idx):
+        return self.validation_step(batch, batch_idx)
+
+    def predict_step(self, batch, batch_idx=0):
+        inputs = batch[0] if isinstance(batch, (tuple, list)) else batch
+        return self.forward(inputs)
+
+
+def make_config(act_bit=4, weight_bit=4, qscheme=1, qnmethod="STE", excluded_layers=(),
+                distillation=False, distillation_loss="Symmetrical KL", quantize_bias=False,
+                freeze_batchnorm=False, fuse_batchnorm=False, name="GDNSQQuant"):
+    """`config.quantization` as the YAML loader would build it (config/*.yaml:49-66)."""
+    params = SimpleNamespace(distillation=distillation, distillation_loss=distillation_loss,
+                             distillation_teacher=None, qnmethod=qnmethod)
+    quant = SimpleNamespace(name=name, qscheme=qscheme, act_bit=act_bit, weight_bit=weight_bit,
+                            freeze_batchnorm=freeze_batchnorm, fuse_batchnorm=fuse_batchnorm,
+                            quantize_bias=quantize_bias, excluded_layers=list(excluded_layers),
+                            calibration=SimpleNamespace(act_bit=10, weight_bit=10), params=params)
+    return SimpleNamespace(quantization=quant)
+
+
+# ------------------------------------------------------------------ models
+class _CifarBlock(nn.Module):
+    """3x3-3x3 residual block with the parameter-free (option A) shortcut."""
+
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.pad = (cout - cin) // 2 if (stride != 1 or cin != cout) else None
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        sc = x if self.pad is None else F.pad(x[:, :, ::2, ::2], (0, 0, 0, 0, self.pad, self.pad))
+        return F.relu(out + sc)
+
+
+class CifarResNet(nn.Module):
+    """ResNet-20/32/.. for 32x32 inputs (He et al. 2015, 6n+2 layers, 16/32/64 channels) —
+    same topology and module names (conv1, layer1..3, linear) as the reference's in-tree
+    src/models/cls/resnet/resnet_cifar.py:99-136, so the configs' excluded_layers apply."""
+
+    def __init__(self, n=3, num_classes=10):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 16, 3, 1, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(16)
+        cin, layers = 16, []
+        for i, (c, s) in enumerate(((16, 1), (32, 2), (64, 2))):
+            blocks = []
+            for b in range(n):
+                blocks.append(_CifarBlock(cin, c, s if b == 0 else 1))
+                cin = c
+            layers.append(nn.Sequential(*blocks))
+        self.layer1, self.layer2, self.layer3 = layers
+        self.linear = nn.Linear(64, num_classes)
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.kaiming_normal_(m.weight)
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.layer3(self.layer2(self.layer1(out)))
+        out = F.adaptive_avg_pool2d(out, 1).flatten(1)
+        return self.linear(out)
+
+
+def build_model(name: str, num_classes: Optional[int] = None) -> nn.Module:
+    if name == "resnet18":
+        import torchvision
+        return torchvision.models.resnet18(num_classes=num_classes or 1000)
+    if name == "resnet20":
+        return CifarResNet(3, num_classes or 10)
+    raise ValueError(name)
+
+
+EXCLUDED = {"resnet18": ("conv1", "fc"), "resnet20": ("conv1", "linear")}
+
+
+# ------------------------------------------------------------------ calibration
+@torch.no_grad()
+def calibrate(qmodel: LModule, batch, act_bits=10, weight_bits=10):
+    """Effect of Trainer.calibrate on one batch: weights get
+    log_wght_s = max(log_wght_s, log2((max-min)/(2^bits-1))) per channel
+    (minmaxobserver.py:69-88); every NoisyAct gets act_b=min, log_act_s=log2(range/(2^bits-1)),
+    log_act_q=log_act_s+bits from the min/max of its input (minmaxobserver.py:39-66),
+    zero-range activations are frozen ("pruned")."""
+    model = qmodel.model
+    for m in model.modules():
+        if isinstance(m, (NoisyConv2d, NoisyLinear)):
+            w = m.weight.detach()
+            if m.log_wght_s.numel() > 1:
+                flat = w.reshape(w.shape[0], -1)
+                rng = (flat.amax(1) - flat.amin(1)).reshape(m.log_wght_s.shape)
+            else:
+                rng = (w.max() - w.min()).reshape(m.log_wght_s.shape)
+            m.log_wght_s.data = torch.max(m.log_wght_s.data, torch.log2(rng / (2 ** weight_bits - 1)))
+    stats, hooks = {}, []
+    for m in model.modules():
+        if isinstance(m, NoisyAct):
+            hooks.append(m.register_forward_hook(
+                lambda mod, inp, out: stats.__setitem__(mod, (inp[0].min(), inp[0].max()))))
+    was_training = model.training
+    model.eval()
+    model(batch)
+    model.train(was_training)
+    for h in hooks:
+        h.remove()
+    for m, (mn, mx) in stats.items():
+        if float(mx - mn) > 0:
+            log_s = torch.log2((mx - mn) / (2 ** act_bits - 1))
+            m.act_b.data.fill_(float(mn))
+            m.log_act_s.data.fill_(float(log_s))
+            m.log_act_q.data.fill_(float(log_s) + act_bits)
+        else:
+            for p in (m.log_act_q, m.log_act_s, m.act_b):
+                p.requires_grad_(False)
+            m.log_act_q.data.zero_(); m.log_act_s.data.zero_(); m.act_b.data.fill_(float(mn))
+
+
+# ------------------------------------------------------------------ build + fit
+def build_qat(model_name="resnet18", device="cuda", qnmethod="STE", act_bit=4, weight_bit=4,
+              distillation=True, num_classes=None, lr=3e-4, calib_batch=None):
+    """FP model → LModule → Quantizer(config)().quantize(lm) → calibrated, on `device`."""
+    from .quantization.quantizer import Quantizer
+    model = build_model(model_name, num_classes).to(device)
+    lm = LModule(model, nn.CrossEntropyLoss(), torch.optim.RAdam, lr)
+    cfg = make_config(act_bit=act_bit, weight_bit=weight_bit, qscheme=1, qnmethod=qnmethod,
+                      excluded_layers=EXCLUDED[model_name], distillation=distillation)
+    qmodel = Quantizer(cfg)().quantize(lm, in_place=True)
+    qmodel.to(device)
+    if calib_batch is not None:
+        calibrate(qmodel, calib_batch)
+    return qmodel
+
+
+def fit_steps(qmodel: LModule, batches, ddp: bool = False, device=None, on_step=None,
+              sync_bn: bool = False):
+    """Run the training steps in Lightning's order.  `batches`: iterable of (inputs, target).
+    Under DDP the quantized model is wrapped like Lightning's DDPStrategy does
+    (find_unused_parameters=True: the reference's never-used `log_b_s`, trainer.py:93-95)."""
+    if ddp:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        if sync_bn:
+            qmodel.model = nn.SyncBatchNorm.convert_sync_batchnorm(qmodel.model)
+        inner = qmodel.model
+        qmodel.model = DDP(inner, device_ids=[device.index] if device is not None else None,
+                           find_unused_parameters=True, gradient_as_bucket_view=True)
+    opt = qmodel.configure_optimizers()
+    qmodel.train()
+    if hasattr(qmodel, "wrapped_criterion"):
+        qmodel.wrapped_criterion.train()
+    for i, batch in enumerate(batches):
+        loss = qmodel.training_step(batch, i)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        if on_step is not None:
+            on_step(i, loss)
+    return qmodel

@@ -1,0 +1,68 @@
+"""Bit-width constraint losses — mirror of the reference's
+src/quantization/gdnsq/gdnsq_loss.py:6-168 (``PotentialLoss`` with a prediction/target
+pair, ``PotentialLossNoPred`` with a precomputed base loss).
+
+    ploss = calib_mul * l1 * (wmul*wloss + amul*aloss) + l2 * rloss
+    wloss = mean(max(0, (log_w_range - log_wght_s) - (w_target - eps))^p)   (same for act)
+
+Row (f)-1 of SURVEY.md §8: host-side glue on O(#channels) tensors, plain PyTorch."""
+import torch
+import torch.nn as nn
+
+
+class _PotentialBase(nn.Module):
+    def __init__(self, criterion, p=1, a=8, w=4, lossless=False) -> None:
+        super().__init__()
+        self.criterion = criterion
+        self.s_weight_loss = torch.tensor(0)
+        self.s_act_loss = torch.tensor(0)
+        self.weight_reg_loss = torch.tensor(0)
+        self.p = torch.tensor(p)
+        self.at = a
+        self.wt = w
+        self.lossless = lossless
+        self.l_eps = torch.tensor(1e-3)
+        self.r_eps = torch.tensor(1e-3)
+        self.aloss = torch.tensor(1.0)
+        self.wloss = torch.tensor(1.0)
+        self.loss_sum = 0.0
+        self.cnt = 1
+        self.t = 0.0
+
+    def _combine(self, base_loss, las, laq, lws, lwq):
+        self.base_loss = base_loss
+        z = torch.tensor(0)
+        wloss0 = torch.max(z, (lwq - lws) - (self.wt - self.l_eps)).pow(self.p)
+        wloss = wloss0.mean()
+        wact = (wloss0 > 0).sum()          # active weight constraints
+        aloss0 = torch.max(z, (laq - las) - (self.at - self.l_eps)).pow(self.p)
+        aloss = aloss0.mean()
+        aact = (aloss0 > 0).sum()          # active activation constraints
+        rloss = base_loss.pow_(self.p)
+        calib_mul = self.loss_sum / self.cnt
+        wmul = (wact + self.l_eps) / (wact + aact + self.l_eps)
+        amul = (aact + self.l_eps) / (wact + aact + self.l_eps)
+        l1, l2 = (1.0, self.t) if self.lossless else (self.t, 1.0)
+        ploss = calib_mul * l1 * (wmul * wloss + amul * aloss) + l2 * rloss
+        if self.training:
+            self.loss_sum += rloss.detach()
+            self.cnt += 1
+        self.wloss, self.aloss, self.rloss = wloss, aloss, rloss
+        self.s_weight_loss = -lws.mean()
+        self.q_weight_loss = lwq.mean()
+        self.s_act_loss = -las.mean()
+        self.q_act_loss = laq.mean()
+        self.weight_reg_loss = (lwq - lws).max()
+        return ploss
+
+
+class PotentialLoss(_PotentialBase):
+    def forward(self, output, target):
+        """output = (prediction, log_act_s, log_act_q, log_wght_s, log_w)"""
+        return self._combine(self.criterion(output[0], target), *output[1:5])
+
+
+class PotentialLossNoPred(_PotentialBase):
+    def forward(self, output):
+        """output = (base_loss, log_act_s, log_act_q, log_wght_s, log_w)"""
+        return self._combine(output[0], *output[1:5])

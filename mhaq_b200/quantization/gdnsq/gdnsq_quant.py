@@ -1,0 +1,232 @@
+"""``GDNSQQuant`` — the quantizer plugin; mirror of the reference's
+src/quantization/gdnsq/gdnsq_quant.py:30-545 built on the sm_100a layer wrappers.
+
+``quantize(lmodel, in_place)`` performs the same model surgery: every ``nn.Conv2d`` /
+``nn.Linear`` that is not excluded (and is not a 1x1 convolution, gdnsq_quant.py:126) is
+replaced by ``nn.Sequential(OrderedDict(activations_quantizer=NoisyAct(...), "0"=Noisy*))``
+sharing the original ``weight``/``bias`` Parameters; activations are signed unless the
+preceding module (``named_modules`` order) is an ``nn.ReLU``; the training / validation /
+test steps of the module are re-bound on the instance; ``wrapped_criterion`` is the
+``PotentialLoss`` bit-width constraint.  Reference quirk kept: ``NoisyAct`` is built without
+``qnmethod`` (gdnsq_quant.py:508-511), so activations always use the STE/GDNSQ estimator and
+only weights use the configured one.
+
+``lmodel`` is duck-typed (Lightning is optional and absent from this image): anything with
+``.model``, ``.criterion``, ``.training_step``, ``.validation_step``, ``.test_step``,
+``.predict_step``, ``.log`` and ``.lr`` works — a ``lightning.LightningModule`` or
+``mhaq_b200.harness.LModule``.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from copy import deepcopy
+from operator import attrgetter
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ...aux.qutils import attrsetter, is_biased
+from ...aux.types import QScheme
+from ..abc.abc_quant import BaseQuant
+from .distill_losses import get_distillation_loss
+from .gdnsq_loss import PotentialLoss, PotentialLossNoPred
+from .gdnsq_utils import QNMethod
+from .layers.gdnsq_act import NoisyAct
+from .layers.gdnsq_conv2d import NoisyConv2d
+from .layers.gdnsq_linear import NoisyLinear
+from .utils.model_helper import ModelHelper
+
+_TRAIN_LOGS = (("Loss/Base train loss", "base_loss", True), ("Loss/Wloss", "wloss", False),
+               ("Loss/Aloss", "aloss", False), ("Loss/Weight reg loss", "weight_reg_loss", False))
+
+
+def _as_qscheme(v):
+    return v if isinstance(v, QScheme) else QScheme(int(v))
+
+
+class GDNSQQuant(BaseQuant):
+    def __init__(self, config):
+        super().__init__(config)
+
+    def module_mappings(self):
+        return {nn.Conv2d: NoisyConv2d, nn.Linear: NoisyLinear}
+
+    def _init_config(self):
+        if self.config:
+            self.quant_config = qc = self.config.quantization
+            self.act_bit = qc.act_bit
+            self.weight_bit = qc.weight_bit
+            self.excluded_layers = qc.excluded_layers
+            self.qscheme = _as_qscheme(qc.qscheme)
+            self.quant_bias = qc.quantize_bias
+
+    # ------------------------------------------------------------------ losses
+    def get_loss(self, qmodel):
+        params = self.config.quantization.params
+        if params.distillation:
+            return get_distillation_loss(params.distillation_loss)
+        return qmodel.criterion
+
+    # ------------------------------------------------------------------ surgery
+    def quantize(self, lmodel, in_place=False):
+        qc = self.config.quantization
+        distill = bool(qc.params.distillation)
+        self.fusebn = qc.fuse_batchnorm
+        if distill:
+            if getattr(qc.params, "distillation_teacher", None):
+                raise NotImplementedError("external distillation teachers are not supported; "
+                                          "the teacher is a frozen copy of the FP model")
+            tmodel = deepcopy(lmodel).eval()
+        qmodel = lmodel if in_place else deepcopy(lmodel)
+
+        names, kinds = zip(*[(n, type(m)) for n, m in qmodel.model.named_modules()])
+
+        qmodel._noise_ratio = torch.tensor(1.0)
+        qmodel.qscheme = self.qscheme
+        loss_cls = PotentialLoss if distill else PotentialLossNoPred
+        if distill:
+            qmodel.tmodel = tmodel.requires_grad_(False)
+        qmodel.wrapped_criterion = loss_cls(criterion=self.get_loss(qmodel), p=1, a=self.act_bit,
+                                            w=self.weight_bit)
+        qmodel.noise_ratio = GDNSQQuant.noise_ratio.__get__(qmodel, type(qmodel))
+
+        # re-bind the steps on the instance (gdnsq_quant.py:106-120)
+        if distill:
+            qmodel.training_step = GDNSQQuant.distillation_noisy_training_step.__get__(
+                qmodel, type(qmodel))
+        else:
+            qmodel.training_step = GDNSQQuant.noisy_train_decorator(qmodel.training_step)
+        qmodel.validation_step = GDNSQQuant.noisy_val_decorator(qmodel.validation_step)
+        qmodel.test_step = GDNSQQuant.noisy_test_decorator(qmodel.test_step)
+
+        for layer in self._get_layers(qmodel.model, exclude_layers=self.excluded_layers):
+            module = attrgetter(layer)(qmodel.model)
+            # 1x1 convolutions are never quantized (gdnsq_quant.py:126).  nn.Linear has no
+            # kernel_size: the reference raises AttributeError here for an un-excluded Linear
+            # (SURVEY.md quirk 2); this build quantizes it instead.
+            if getattr(module, "kernel_size", None) == (1, 1):
+                continue
+            idx = names.index(layer)
+            if idx + 1 < len(kinds) and issubclass(kinds[idx + 1], nn.BatchNorm2d) and self.fusebn:
+                self.fuse_conv_bn(qmodel.model, layer, names[idx + 1])
+            signed = not issubclass(kinds[idx - 1], nn.ReLU)
+            attrsetter(layer)(qmodel.model, self._quantize_module(module, signed_activations=signed))
+
+        if qc.freeze_batchnorm:
+            GDNSQQuant.freeze_all_batchnorm_layers(qmodel)
+        return qmodel
+
+    @staticmethod
+    def freeze_all_batchnorm_layers(model, freeze=True):
+        for m in model.modules():
+            if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d, nn.BatchNorm3d)):
+                m.eval()
+                m.weight.requires_grad = not freeze
+                m.bias.requires_grad = not freeze
+
+    def fuse_conv_bn(self, model: nn.Module, conv_name: str, bn_name: str):
+        """Fold an eval-mode BatchNorm into the preceding convolution (gdnsq_quant.py:161-184)."""
+        conv, bn = attrgetter(conv_name)(model), attrgetter(bn_name)(model)
+        w = conv.weight.clone()
+        b = conv.bias.clone() if conv.bias is not None else torch.zeros(conv.out_channels, device=w.device)
+        k = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        conv.weight.data = w * k.view([-1] + [1] * (w.dim() - 1))
+        conv.bias = nn.Parameter(bn.bias + (b - bn.running_mean) * k)
+        attrsetter(bn_name)(model, nn.Identity())
+
+    @staticmethod
+    def noise_ratio(self, x=None):
+        if x is not None:
+            for m in self.modules():
+                if hasattr(m, "_noise_ratio"):
+                    m._noise_ratio.data = x.clone().detach()
+        return self._noise_ratio
+
+    # ------------------------------------------------------------------ steps
+    @staticmethod
+    def _log_train(self, loss):
+        self.log("Loss/Train loss", loss, prog_bar=True, sync_dist=True)
+        for name, attr, bar in _TRAIN_LOGS:
+            self.log(name, getattr(self.wrapped_criterion, attr), prog_bar=bar, sync_dist=True)
+        self.log("LR", self.lr, prog_bar=True, sync_dist=True)
+
+    @staticmethod
+    def noisy_train_decorator(train_step):
+        self = train_step.__self__
+
+        def wrapper(batch, batch_idx):
+            outputs = (train_step(batch, batch_idx),
+                       *ModelHelper.get_model_values(self.model, self.qscheme))
+            loss = self.wrapped_criterion(outputs)
+            GDNSQQuant._log_train(self, loss)
+            return loss
+
+        return wrapper
+
+    @staticmethod
+    def noisy_step(self, x):
+        return (self.forward(x), *ModelHelper.get_model_values(self.model, self.qscheme))
+
+    @staticmethod
+    def distillation_noisy_training_step(self, batch, batch_idx):
+        inputs, targets = batch
+        outputs = GDNSQQuant.noisy_step(self, inputs)
+        self.tmodel.eval()
+        fp_outputs = self.tmodel.predict_step(inputs, batch_idx)
+        loss = self.wrapped_criterion(outputs, fp_outputs)
+        self.log("Loss/FP loss", F.cross_entropy(fp_outputs, targets), sync_dist=True)
+        GDNSQQuant._log_train(self, loss)
+        return loss
+
+    @staticmethod
+    def noisy_val_decorator(val_step):
+        self = val_step.__self__
+
+        def wrapper(*args):
+            from .utils import model_stats   # validation-time statistics (row (f)-3)
+            loss = val_step(*args)
+            self.log("Loss/Validation loss", loss, prog_bar=False, sync_dist=True)
+            for name, fn in model_stats.VALIDATION_STATS:
+                self.log(name, fn(self.model), prog_bar=False, sync_dist=True)
+            return loss
+
+        return wrapper
+
+    @staticmethod
+    def noisy_test_decorator(test_step):
+        def wrapper(*args):
+            return test_step(*args)
+
+        return wrapper
+
+    # ------------------------------------------------------------------ per-layer
+    def _quantize_module(self, module, signed_activations):
+        self.qnmethod = QNMethod[self.quant_config.params.qnmethod]
+        if isinstance(module, nn.Conv2d):
+            qmodule = self._quantize_module_conv2d(module)
+        elif isinstance(module, nn.Linear):
+            qmodule = self._quantize_module_linear(module)
+        else:
+            raise NotImplementedError(f"Module not supported {type(module)}")
+        qmodule.weight = module.weight
+        if is_biased(module):
+            qmodule.bias = module.bias
+        return self._get_quantization_sequence(qmodule, signed_activations)
+
+    def _get_quantization_sequence(self, qmodule, signed_activations):
+        disabled = self.config.quantization.act_bit == -1
+        return nn.Sequential(OrderedDict([
+            ("activations_quantizer", NoisyAct(signed=signed_activations, disable=disabled)),
+            ("0", qmodule),
+        ]))
+
+    def _quantize_module_conv2d(self, module: nn.Conv2d):
+        return NoisyConv2d(module.in_channels, module.out_channels, module.kernel_size, module.stride,
+                           module.padding, module.dilation, module.groups, is_biased(module),
+                           module.padding_mode, qscheme=self.qscheme, log_s_init=-12,
+                           quant_bias=self.quant_bias, qnmethod=self.qnmethod)
+
+    def _quantize_module_linear(self, module: nn.Linear):
+        return NoisyLinear(module.in_features, module.out_features, is_biased(module),
+                           qscheme=self.qscheme, log_s_init=-12, qnmethod=self.qnmethod)

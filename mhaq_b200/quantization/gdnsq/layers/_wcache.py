@@ -46,16 +46,17 @@ class WeightQuantCache:
 
     def store(self, key, value):
         self.key, self.value = key, value
-        if torch.is_tensor(value) and value.requires_grad:
-            cache = self
+        cache = self
 
-            def _drop(grad, _key=key):
-                # backward through this entry is running: its graph is about to be freed
-                if cache.key == _key:
-                    cache.key, cache.value = None, None
-                return grad
+        def _drop(grad, _key=key):
+            # backward through this entry is running: its graph is about to be freed
+            if cache.key == _key:
+                cache.key, cache.value = None, None
+            return grad
 
-            value.register_hook(_drop)
+        for t in (value if isinstance(value, (tuple, list)) else (value,)):
+            if torch.is_tensor(t) and t.requires_grad and t.grad_fn is not None:
+                t.register_hook(_drop)
 
     def clear(self):
         self.key, self.value = None, None

@@ -1,0 +1,39 @@
+"""``ModelHelper.get_model_values`` — mirror of the reference's
+src/quantization/gdnsq/utils/model_helper.py:11-76: collects, per quantized layer, the
+log-domain scale parameters and the differentiable weight range
+``log2(max - min + 2^log_wght_s)`` that ``PotentialLoss`` constrains."""
+import torch
+from torch import nn
+
+from ....aux.types import QScheme
+from ..layers.gdnsq_act import NoisyAct
+from ..layers.gdnsq_conv2d import NoisyConv2d
+from ..layers.gdnsq_linear import NoisyLinear
+
+
+class ModelHelper:
+    @staticmethod
+    def get_model_values(model: nn.Module, qscheme: QScheme = QScheme.PER_TENSOR):
+        log_wght_s, log_w_n_b, log_act_q, log_act_s = [], [], [], []
+        for _, m in model.named_modules():
+            if isinstance(m, (NoisyConv2d, NoisyLinear)):
+                if not m.log_wght_s.requires_grad:
+                    continue
+                if qscheme == QScheme.PER_CHANNEL:
+                    dims = tuple(range(1, m.weight.dim()))
+                    log_wght_s.append(m.log_wght_s.ravel())
+                    mn, mx = m.weight.amin(dims), m.weight.amax(dims)
+                else:
+                    log_wght_s.append(m.log_wght_s)
+                    mn, mx = m.weight.amin(), m.weight.amax()
+                # one LSB of head-room against overflow (model_helper.py:43-44)
+                log_w_n_b.append(torch.log2(mx - mn + torch.exp2(m.log_wght_s.ravel())))
+            elif isinstance(m, NoisyAct):
+                if m.log_act_s.requires_grad:
+                    log_act_q.append(m.log_act_q)
+                    log_act_s.append(m.log_act_s)
+        if qscheme == QScheme.PER_TENSOR:
+            return (torch.stack(log_act_s).ravel(), torch.stack(log_act_q).ravel(),
+                    torch.stack(log_wght_s).ravel(), torch.stack(log_w_n_b).ravel())
+        return (torch.cat(log_act_s), torch.cat(log_act_q), torch.cat(log_wght_s),
+                torch.cat(log_w_n_b))

@@ -1,0 +1,152 @@
+"""GPU: layer wrappers and the plugin flow on the sm_100a kernels vs the oracle."""
+import math
+
+import pytest
+import torch
+from torch import nn
+
+from oracle import fq_oracle as O
+from oracle.checks import assert_bit_exact, assert_close_rel
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _cpu_exp2_pin(module):
+    """Make exp2 of the log-parameters exact on both devices (integer-valued logs)."""
+    for n, p in module.named_parameters():
+        if n.startswith("log_"):
+            p.data.round_()
+
+
+def test_noisy_act_matches_oracle_train_and_eval():
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_act import NoisyAct
+    torch.manual_seed(0)
+    x = torch.randn(4, 8, 14, 14) * 2
+    go = torch.randn_like(x)
+    act = NoisyAct(signed=True).cuda()
+    with torch.no_grad():
+        act.log_act_s.fill_(-2.0); act.log_act_q.fill_(2.0); act.act_b.fill_(-1.75)
+    act.train()
+    xg = x.cuda().requires_grad_(True)
+    torch.manual_seed(5)
+    y = act(xg)
+    y.backward(go.cuda())
+    # oracle with the same parameters; LSQ-free comparison of the deterministic parts
+    ls = torch.tensor([-2.0], requires_grad=True); lq = torch.tensor([2.0], requires_grad=True)
+    b = torch.tensor([-1.75], requires_grad=True)
+    xo = x.clone().requires_grad_(True)
+    r0 = torch.zeros_like(x)           # noise only enters d/d log_act_s
+    yo = O.act_fake_quant(xo, ls, lq, b, noise=r0)
+    yo.backward(go)
+    assert_bit_exact(y, yo, "y")
+    assert_bit_exact(xg.grad, xo.grad, "gx")
+    assert_close_rel(act.log_act_q.grad, lq.grad, 1e-5, "g_log_act_q", abs_floor=2e-6)
+    assert_close_rel(act.act_b.grad, b.grad, 1e-5, "g_act_b", abs_floor=2e-5)
+    # eval: one pass gives y, bw, and the validity check
+    act.eval()
+    with torch.no_grad():
+        ye = act(x.cuda())
+    assert_bit_exact(ye, yo, "y eval")
+    codes = O.quantize(x, torch.exp2(ls), b, b, b + torch.exp2(lq) - torch.exp2(ls)).detach()
+    assert_bit_exact(act.bw, O.act_bit_width(codes), "bw")
+    with pytest.raises(AssertionError, match="integer values"):
+        act(torch.full((8,), float("nan"), device="cuda"))
+
+
+@pytest.mark.parametrize("scheme,method", [("PER_CHANNEL", "STE"), ("PER_CHANNEL", "LSQ"),
+                                           ("PER_CHANNEL", "AEWGS"), ("PER_TENSOR", "LSQ")])
+def test_noisy_conv_weight_path_matches_oracle(scheme, method):
+    from mhaq_b200.aux.types import QScheme
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
+    torch.manual_seed(1)
+    conv = NoisyConv2d(16, 32, 3, padding=1, bias=True, qscheme=QScheme[scheme],
+                       qnmethod=QNMethod[method]).cuda()
+    with torch.no_grad():
+        conv.weight.mul_(3.0)
+        conv.log_wght_s.fill_(-4.0)
+    conv.train()
+    wq, _ = conv.quantized_weight()
+    go = torch.randn(wq.shape)
+    wq.backward(go.cuda())
+    w = conv.weight.detach().cpu().clone().requires_grad_(True)
+    ls = conv.log_wght_s.detach().cpu().clone().requires_grad_(True)
+    wo = O.weight_fake_quant(w, ls, scheme == "PER_CHANNEL", method, noise=torch.zeros_like(w))
+    wo.backward(go)
+    assert_bit_exact(wq, wo, "wq")
+    if method == "LSQ":
+        assert_close_rel(conv.weight.grad, w.grad, 1e-5, "g_weight", abs_floor=2e-5)
+        assert_close_rel(conv.log_wght_s.grad, ls.grad, 1e-5, "g_log_wght_s", abs_floor=5e-5)
+    elif method == "AEWGS":
+        assert_close_rel(conv.weight.grad, w.grad, 1e-5, "g_weight", abs_floor=2e-5)
+
+
+def test_weight_cache_semantics():
+    from mhaq_b200.aux.types import QScheme
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
+    conv = NoisyConv2d(8, 8, 3, padding=1, qscheme=QScheme.PER_CHANNEL, qnmethod=QNMethod.LSQ).cuda()
+    with torch.no_grad():
+        conv.log_wght_s.fill_(-3.0)
+    x = torch.randn(2, 8, 6, 6, device="cuda")
+    c = conv._wq_cache
+    # no_grad: one quantization for any number of batches
+    conv.eval()
+    with torch.no_grad():
+        y1 = conv(x); y2 = conv(x); y3 = conv(x)
+    assert (c.misses, c.hits) == (1, 2) and torch.equal(y1, y3)
+    # an in-place parameter update (optimizer step) invalidates
+    with torch.no_grad():
+        conv.weight.add_(0.01)
+        conv(x)
+    assert c.misses == 2
+    # training: reused by forward calls preceding one backward, dropped by that backward
+    conv.train()
+    out = conv(x).sum() + conv(x).sum()
+    assert (c.misses, c.hits) == (3, 3)
+    out.backward()
+    assert c.value is None
+    g_two = conv.weight.grad.clone()
+    conv.weight.grad = None
+    (conv(x).sum() * 2).backward()
+    torch.testing.assert_close(g_two, conv.weight.grad, rtol=1e-5, atol=1e-6)
+    # re-binding a parameter (what calibration does) invalidates as well
+    conv.log_wght_s = nn.Parameter(conv.log_wght_s.detach().clone() + 1)
+    conv(x).sum().backward()
+    assert c.misses >= 5
+    assert "_wq_cache" not in conv.state_dict()
+
+
+def test_resnet20_qat_steps_run_and_learnable_params_get_grads():
+    from mhaq_b200 import harness
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    x = torch.randn(32, 3, 32, 32, device=dev)
+    t = torch.randint(0, 10, (32,), device=dev)
+    for method, distill in (("STE", False), ("AEWGS", True), ("LSQ", False)):
+        q = harness.build_qat("resnet20", dev, qnmethod=method, distillation=distill, calib_batch=x)
+        seen = {}
+
+        def on_step(i, loss, seen=seen):
+            seen[i] = float(loss.detach())
+        # one manual step: every scale parameter receives a (finite) gradient
+        q.train()
+        q.training_step((x, t), 0).backward()
+        scale_grads = {n: p.grad for n, p in q.model.named_parameters()
+                       if "log_wght_s" in n or "log_act_s" in n}
+        assert len(scale_grads) == 36
+        assert all(g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
+                   for g in scale_grads.values()), "every scale parameter must receive a gradient"
+        q.zero_grad(set_to_none=True)
+        harness.fit_steps(q, [(x, t)] * 3, on_step=on_step)
+        assert len(seen) == 3 and all(math.isfinite(v) for v in seen.values())
+        # log_b_s is never used, exactly like the reference
+        assert all(p.grad is None for n, p in q.model.named_parameters() if n.endswith("log_b_s"))
+        assert "Loss/Train loss" in q.logged and "Loss/Wloss" in q.logged
+        # validation step with the statistics of the patched step
+        q.eval()
+        with torch.no_grad():
+            q.validation_step((x, t), 0)
+        assert "Actual activations max bit widths" in q.logged
+        assert float(q.logged["Actual weights max bit width"]) <= 10.01   # calibrated to 10 bits

@@ -1,0 +1,91 @@
+"""CPU: the plugin surface (model surgery, state-dict layout, config plumbing) needs no GPU —
+no kernel is launched until a forward pass."""
+import pytest
+import torch
+from torch import nn
+
+from mhaq_b200 import harness
+from mhaq_b200.aux.types import QScheme
+from mhaq_b200.quantization.quantizer import Quantizer
+from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+from mhaq_b200.quantization.gdnsq.layers.gdnsq_act import NoisyAct
+from mhaq_b200.quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
+
+
+def _quantized(model_name, **kw):
+    lm = harness.LModule(harness.build_model(model_name), nn.CrossEntropyLoss())
+    cfg = harness.make_config(excluded_layers=harness.EXCLUDED[model_name], **kw)
+    return Quantizer(cfg)().quantize(lm, in_place=True)
+
+
+def test_resnet20_surgery_and_state_dict_layout():
+    q = _quantized("resnet20", qnmethod="AEWGS")
+    convs = [(n, m) for n, m in q.model.named_modules() if isinstance(m, NoisyConv2d)]
+    acts = [m for m in q.model.modules() if isinstance(m, NoisyAct)]
+    assert len(convs) == 18 and len(acts) == 18
+    assert isinstance(q.model.conv1, nn.Conv2d) and not isinstance(q.model.conv1, NoisyConv2d)
+    assert isinstance(q.model.linear, nn.Linear)
+    sd = q.model.state_dict()
+    name = "layer1.0.conv1"
+    for k, shape in ((f"{name}.activations_quantizer.log_act_q", (1,)),
+                     (f"{name}.activations_quantizer.act_b", (1,)),
+                     (f"{name}.activations_quantizer.log_act_s", (1,)),
+                     (f"{name}.0.weight", (16, 16, 3, 3)),
+                     (f"{name}.0.log_wght_s", (16, 1, 1, 1)),
+                     (f"{name}.0.log_b_s", (1,)),
+                     (f"{name}.0._noise_ratio", (1,))):
+        assert tuple(sd[k].shape) == shape, k
+    # init values (gdnsq_quant.py:532, gdnsq_act.py:12-25)
+    assert float(sd[f"{name}.0.log_wght_s"].flatten()[0]) == -12
+    assert float(sd[f"{name}.activations_quantizer.log_act_s"]) == -10
+    assert float(sd[f"{name}.activations_quantizer.log_act_q"]) == 10
+    # weights use the configured estimator, activations always STE (reference quirk 1)
+    assert convs[0][1].Q.qnmethod == QNMethod.AEWGS and acts[0].Q.qnmethod == QNMethod.STE
+    assert convs[0][1].qscheme == QScheme.PER_CHANNEL
+    # the in-tree CIFAR ResNet uses functional relu: every activation is signed
+    assert all(a.signed for a in acts)
+    assert hasattr(q, "wrapped_criterion") and q.wrapped_criterion.at == 4 and q.wrapped_criterion.wt == 4
+
+
+def test_resnet18_signedness_and_1x1_skipped():
+    q = _quantized("resnet18", distillation=True)
+    convs = {n: m for n, m in q.model.named_modules() if isinstance(m, NoisyConv2d)}
+    assert len(convs) == 16                                # 3 downsample 1x1 convs skipped
+    assert isinstance(q.model.layer2[0].downsample[0], nn.Conv2d)
+    assert not isinstance(q.model.layer2[0].downsample[0], NoisyConv2d)
+    # torchvision registers `relu` before conv2 in named_modules order: conv2 unsigned, conv1 signed
+    b = q.model.layer1[0]
+    assert b.conv1.activations_quantizer.signed and not b.conv2.activations_quantizer.signed
+    assert b.conv2.activations_quantizer.act_b.requires_grad is False
+    assert hasattr(q, "tmodel") and not any(p.requires_grad for p in q.tmodel.parameters())
+    # weight / bias Parameters are shared with the original conv, not copied
+    n_fp = sum(p.numel() for p in harness.build_model("resnet18").parameters())
+    n_q = sum(p.numel() for n, p in q.model.named_parameters()
+              if not any(t in n for t in ("log_", "act_b", "_noise_ratio")))
+    assert n_fp == n_q
+
+
+def test_excluded_layer_must_exist():
+    lm = harness.LModule(harness.build_model("resnet20"), nn.CrossEntropyLoss())
+    cfg = harness.make_config(excluded_layers=["nope"])
+    with pytest.raises(AttributeError, match="not found"):
+        Quantizer(cfg)().quantize(lm)
+
+
+def test_unknown_estimator_name():
+    lm = harness.LModule(harness.build_model("resnet20"), nn.CrossEntropyLoss())
+    cfg = harness.make_config(excluded_layers=["conv1", "linear"], qnmethod="FOO")
+    with pytest.raises(KeyError):
+        Quantizer(cfg)().quantize(lm)
+
+
+def test_fused_functions_are_placeholders():
+    from mhaq_b200.quantization.gdnsq.gdnsq import QNSTE
+    with pytest.raises(NotImplementedError, match="fused"):
+        QNSTE.apply(torch.zeros(2), torch.ones(1))
+
+
+def test_cpu_forward_fails_loudly():
+    act = NoisyAct()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        act(torch.randn(4, 4))
