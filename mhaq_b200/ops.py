@@ -224,7 +224,14 @@ def aewgs_stats(go, x, L: _Launch, code_grad: bool) -> torch.Tensor:
     check(lib.mhaq_fq_aewgs_stats_finalize_f32(_ptr(ws), geo.n_rows, geo.n_inner, geo.n_ch,
                                                _ptr(stats), _stream()),
           "mhaq_fq_aewgs_stats_finalize_f32")
-    if dist.is_available() and dist.is_initialized():
+    return allreduce_packed_stats(stats)
+
+
+def allreduce_packed_stats(stats: torch.Tensor) -> torch.Tensor:
+    """The one exchange step on the path: AVG all-reduce of the packed [3*n_ch] AEWGS
+    statistics (num | e2 | me) — one collective where the reference issues three
+    (gdnsq.py:126-129).  No-op outside a process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.AVG)
     return stats
 
