@@ -219,7 +219,7 @@ def resnet18_leg(a, dev, world, rank, use_dist):
            "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
            "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1), "n_gpus": world,
            "quantized_act_elems_per_step": 1680896 * B}
-    if rank == 0:
+    if rank == 0 and not use_dist:   # (a rank-local DDP step would dead-lock the other ranks)
         try:   # share of the step spent in the fake-quant kernels (CUPTI kernel times)
             from torch.profiler import profile, ProfilerActivity
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -280,7 +280,8 @@ def run_ours(a):
     use_dist = world > 1
     if use_dist:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     n = 1 << a.log2n
     x, go, scale, zp, lo, hi = make_inputs(a, dev)
     lo_ = -math.inf if lo is None else lo
