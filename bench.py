@@ -171,7 +171,34 @@ def time_region(fn, steps, sync_dist):
 
 
 # ---------------------------------------------------------------------------
-def resnet18_leg(a, dev, world, rank, use_dist):
+class _EagerReferenceBackend:
+    """Bench-only A/B switch: route Quantizer.fake_quant through the reference's eager ATen
+    chain (the oracle port) on the GPU, to time the SAME QAT step the way the reference runs
+    it.  Lives in bench.py on purpose — the product has no such switch."""
+
+    def __enter__(self):
+        from mhaq_b200.quantization.gdnsq import gdnsq as G
+        from oracle import fq_oracle as O
+        self.G, self.saved = G, (G.Quantizer.fake_quant, G.Quantizer.fake_quant_eval)
+
+        def fake_quant(q, value, noise=None):
+            return O.fake_quant(value, q.scale, q.zero_point, q.min_val, q.max_val,
+                                method=q.qnmethod.name, noise=noise)
+
+        def fake_quant_eval(q, value):
+            codes = O.quantize(value, q.scale, q.zero_point, q.min_val, q.max_val)
+            mm = codes.aminmax()
+            return O.dequantize(codes, q.scale, q.zero_point), torch.stack(
+                [mm.min, mm.max, torch.zeros((), device=value.device)])
+
+        G.Quantizer.fake_quant, G.Quantizer.fake_quant_eval = fake_quant, fake_quant_eval
+        return self
+
+    def __exit__(self, *a):
+        self.G.Quantizer.fake_quant, self.G.Quantizer.fake_quant_eval = self.saved
+
+
+def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     """BASELINE configs[3]: torchvision ResNet-18, ImageNet-shaped synthetic batch (256 per GPU,
     224x224), GDNSQ/STE W4A4 per-channel, distillation (Symmetrical KL) from a frozen FP copy,
     RAdam lr 3e-4, fp32 + TF32 convolutions, DDP over NCCL for N > 1 — through
@@ -219,7 +246,7 @@ def resnet18_leg(a, dev, world, rank, use_dist):
            "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
            "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1), "n_gpus": world,
            "quantized_act_elems_per_step": 1680896 * B}
-    if rank == 0 and not use_dist:   # (a rank-local DDP step would dead-lock the other ranks)
+    if rank == 0 and not use_dist and profile_share:   # (a rank-local DDP step would dead-lock the other ranks)
         try:   # share of the step spent in the fake-quant kernels (CUPTI kernel times)
             from torch.profiler import profile, ProfilerActivity
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -394,6 +421,13 @@ def run_ours(a):
     if rank == 0:
         if not a.no_eager_ref:
             out["reference_eager_gpu"] = eager_reference_leg(a, dev)
+            if not a.no_resnet and not use_dist:
+                with _EagerReferenceBackend():
+                    rr = resnet18_leg(a, dev, 1, 0, False, profile_share=False)
+                out["reference_eager_gpu"]["resnet18_w4a4_qat"] = {
+                    "img_per_s": rr["img_per_s"], "ms_per_step": rr["ms_per_step"],
+                    "what": "same QAT step with every fake-quant routed through the reference's eager "
+                            "ATen chain on this GPU"}
         if not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, steps=5, warmup=2)
         if a.sweep:
@@ -482,22 +516,31 @@ def sweep(a, dev):
                     g = lambda: ops._backward_impl(go, x, L, mid, False, None, True, philox=(1, 2))
                     reps = 50 if log2n <= 24 else (20 if log2n <= 28 else 5)
                     res = {}
-                    for nm, fn, by in (("fwd", f, 8), ("bwd", g, 12 + (8 if method == "AEWGS" else 0))):
-                        for _ in range(5):
-                            fn()
-                        # small tensors stay in L2 between iterations: flush with a 256 MB write
-                        flush = torch.empty(64 << 20, dtype=torch.float32, device=dev) if log2n <= 24 else None
-                        ts = []
+                    # tensors that fit the 126 MB L2 are evicted between iterations by a 256 MB
+                    # write; its own time is measured the same way and subtracted.  Launches are
+                    # enqueued back to back so the figure is GPU time, not host launch latency.
+                    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev) if log2n <= 24 else None
+
+                    def timed(body):
+                        for _ in range(3):
+                            body()
+                        torch.cuda.synchronize()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
                         for _ in range(reps):
-                            if flush is not None:
-                                flush.zero_()
-                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-                            ts.append(e0.elapsed_time(e1))
-                        ts.sort()
-                        med = ts[len(ts) // 2]
-                        res[nm] = {"ms_median": round(med, 4), "ms_best": round(ts[0], 4),
-                                   "GBps": round(by * n / med / 1e6, 1), "frac": round(by * n / med / 1e6 / peak, 4)}
+                            body()
+                        e1.record()
+                        torch.cuda.synchronize()
+                        return e0.elapsed_time(e1) / reps
+
+                    t_flush = timed(lambda: flush.zero_()) if flush is not None else 0.0
+                    for nm, fn, by in (("fwd", f, 8), ("bwd", g, 12 + (8 if method == "AEWGS" else 0))):
+                        if flush is not None:
+                            med = max(timed(lambda: (flush.zero_(), fn())) - t_flush, 1e-6)
+                        else:
+                            med = timed(fn)
+                        res[nm] = {"ms_median": round(med, 5), "GBps": round(by * n / med / 1e6, 1),
+                                   "frac": round(by * n / med / 1e6 / peak, 4)}
                     tot = res["fwd"]["ms_median"] + res["bwd"]["ms_median"]
                     by = 20 + (8 if method == "AEWGS" else 0)
                     rows.append({"log2n": log2n, "channels": ch, "method": method, "bits": bits, **res,

@@ -100,7 +100,10 @@ __device__ __forceinline__ QConst load_qconst(const QParams &p, int64_t ch) {
 // touched exactly once per kernel).
 __device__ __forceinline__ float4 ld_stream4(const float *p) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+#ifndef MHAQ_LD_VOLATILE
+#define MHAQ_LD_VOLATILE volatile
+#endif
+    asm MHAQ_LD_VOLATILE("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p));
     return v;
@@ -200,6 +203,73 @@ constexpr float kXHi = 1.2089258196146292e+24f;       // 2^80
 constexpr uint32_t kGoLoBits2m1 = (0x23800000u << 1) - 1u;   // (bits(2^-56) << 1) - 1
 constexpr float kGvHi = 1.2089258196146292e+24f;      // 2^80 (general gradient division)
 __device__ __forceinline__ bool scale_fast_ok(float s) { return s >= kScaleLo && s <= kScaleHi; }
+
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2) -----------------
+// Blackwell issues IEEE round-to-nearest add/mul/fma on TWO fp32 lanes with one
+// instruction (PTX add/sub/mul/fma.rn.f32x2 on a 64-bit register pair; scalar
+// operands broadcast for free in SASS).  Each lane rounds exactly like the scalar
+// instruction, so the arithmetic contract is unchanged while the hot loops — which are
+// issue-slot limited, not pipe limited (profiles/r01_ncu_summary.md) — spend half the
+// issue slots on floating-point work.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 bc2(float a) { return pk2(a, a); }
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// A product whose result feeds an ADD must keep its own rounding (the reference rounds
+// a*b before adding).  ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even
+// though both carry an explicit rounding modifier (it does not do that to the scalar
+// forms; it even rewrites fma2(a,b,-0) back into a fusable multiply) — found by the parity
+// tests.  Such products are therefore formed with two scalar mul.rn.f32 and re-packed.
+__device__ __forceinline__ f32x2 mul2_rounded(f32x2 a, f32x2 b) {
+    float a0, a1, b0, b1;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(b0), "=f"(b1) : "l"(b));
+    return pk2(__fmul_rn(a0, b0), __fmul_rn(a1, b1));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// Packed per-channel constants of the FMA division sequences.  Negated copies stand in
+// for the operand-negate modifiers PTX does not expose on f32x2:
+//   quotient  q' = fma(fma(q, -s, a), y, q)        with q = a*y   (== div_exact; the sign of a
+//             ZERO quotient may differ, which is invisible after code = v + (rint(v) - v))
+//   gradient  gu = fma(fma(go, s, -g), -y, go)     with -g = go*(-s) exactly (== div_of_product,
+//             zero signs included: (+0)*(-y) = -0)
+struct Div2 {
+    f32x2 s, sn, y, yn;
+};
+__device__ __forceinline__ Div2 make_div2(float s, float y) {
+    Div2 d;
+    d.s = bc2(s); d.sn = bc2(-s); d.y = bc2(y); d.yn = bc2(-y);
+    return d;
+}
+__device__ __forceinline__ f32x2 div2_quot(f32x2 a, const Div2 &d) {
+    const f32x2 q = mul2(a, d.y);
+    return fma2(fma2(q, d.sn, a), d.y, q);
+}
 
 // torch.clamp(x, lo, hi): NaN in x propagates; lo > hi yields hi.
 __device__ __forceinline__ float f_clamp(float x, float lo, float hi) {

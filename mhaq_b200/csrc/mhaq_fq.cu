@@ -28,7 +28,7 @@ enum { NOISE_PHILOX = 0, NOISE_EXPLICIT = 1, NOISE_NONE = 2 };
 
 // resident CTAs per SM the backward kernel is compiled for (register cap = 65536/(128*N))
 #ifndef MHAQ_BWD_MIN_CTAS
-#define MHAQ_BWD_MIN_CTAS 7
+#define MHAQ_BWD_MIN_CTAS 5
 #endif
 
 // ===========================================================================
@@ -53,13 +53,20 @@ __device__ __forceinline__ float fwd_elem(float x, const QConst &q, float &code)
 // irrelevant to code = v + (rint(v) - v) = 0, so tiny / denormal u need no guard; huge
 // |x| (> 2^80, incl. inf) is sent to the general path by the caller.
 template <bool CLAMP>
-__device__ __forceinline__ float fwd_elem_fast(float x, const QConst &q, float rcp, float &code) {
-    const float c = CLAMP ? f_clamp(x, q.lo, q.hi) : x;
-    const float u = f_sub(c, q.zp);
-    const float v = div_exact(u, q.s, rcp);
-    const float nz = f_sub(rintf(v), v);
-    code = f_add(v, nz);
-    return f_add(f_mul(code, q.s), q.zp);
+__device__ __forceinline__ void fwd_pair_fast(float x0, float x1, const QConst &q, const Div2 &d,
+                                              f32x2 zpn, f32x2 zp2, float &y0, float &y1, float &c0,
+                                              float &c1) {
+    const float a0 = CLAMP ? f_clamp(x0, q.lo, q.hi) : x0;
+    const float a1 = CLAMP ? f_clamp(x1, q.lo, q.hi) : x1;
+    const f32x2 u = add2(pk2(a0, a1), zpn);              // c - zp
+    const f32x2 v = div2_quot(u, d);                     // u / s
+    float v0, v1;
+    upk2(v, v0, v1);
+    const f32x2 nz = sub2(pk2(rintf(v0), rintf(v1)), v); // round(v) - v
+    const f32x2 code = add2(v, nz);                      // v + noise
+    const f32x2 y = add2(mul2_rounded(code, d.s), zp2);  // code*s, then + zp (two roundings)
+    upk2(y, y0, y1);
+    upk2(code, c0, c1);
 }
 
 __device__ __forceinline__ float absmax4(float m, const float4 &v) {
@@ -75,7 +82,8 @@ fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restr
     for (int64_t t = blockIdx.x; t < g.n_tasks; t += gridDim.x) {
         const Task k = make_task(g, t);
         const QConst q = load_qconst(prm, k.ch);
-        const float rcp = __frcp_rn(q.s);
+        const Div2 dv = make_div2(q.s, __frcp_rn(q.s));
+        const f32x2 zpn = bc2(-q.zp), zp2 = bc2(q.zp);
         const bool fast_ok = VEC && scale_fast_ok(q.s) && (mm_ws == nullptr);
         const float *xr = x + k.row_off;
         float *yr = y ? y + k.row_off : nullptr;
@@ -100,10 +108,8 @@ fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restr
                     for (int u = 0; u < kU; ++u) {
                         float4 cv, yv;
                         if (!huge) {
-                            yv.x = fwd_elem_fast<CLAMP>(xv[u].x, q, rcp, cv.x);
-                            yv.y = fwd_elem_fast<CLAMP>(xv[u].y, q, rcp, cv.y);
-                            yv.z = fwd_elem_fast<CLAMP>(xv[u].z, q, rcp, cv.z);
-                            yv.w = fwd_elem_fast<CLAMP>(xv[u].w, q, rcp, cv.w);
+                            fwd_pair_fast<CLAMP>(xv[u].x, xv[u].y, q, dv, zpn, zp2, yv.x, yv.y, cv.x, cv.y);
+                            fwd_pair_fast<CLAMP>(xv[u].z, xv[u].w, q, dv, zpn, zp2, yv.z, yv.w, cv.z, cv.w);
                         } else {
                             yv.x = fwd_elem(xv[u].x, q, cv.x);
                             yv.y = fwd_elem(xv[u].y, q, cv.y);
@@ -312,6 +318,75 @@ __device__ __forceinline__ float bwd_elem(float x, float go, float rv, uint32_t 
     return gx;
 }
 
+// Packed (two elements per FP instruction) version of bwd_elem<.., FAST=true, CODEGRAD=false>
+// for the STE / LSQ estimators — the hot variants (every activation, most weights).
+// Same fp32 operations element by element; g is carried NEGATED (gn = go*(-s) == -RN(go*s)
+// exactly) so that no operand-negate modifier is needed:
+//   r  = go*s - g           = fma2(go, s, gn)            (exact)
+//   gu = RN(g/s)            = fma2(r, -y, go)            (div_of_product, zero signs included)
+//   t2 = -RN(g*RN(v/s))     = mul2(gn, div2_quot(v))
+// The noise / LSQ sum is accumulated with the opposite sign and negated at the flush.
+struct Acc2 {
+    f32x2 se, sn, sz;
+};
+struct PairConst {
+    Div2 d;
+    f32x2 zpn, c, half;
+};
+
+template <int METHOD, bool CLAMP, int NOISE>
+__device__ __forceinline__ void bwd_pair_fast(float x0, float x1, float go0, float go1, float rn0,
+                                              float rn1, uint32_t sf0, uint32_t sf1, const QConst &q,
+                                              const PairConst &pc, Acc2 &a2, Acc &acc, float &o0,
+                                              float &o1) {
+    float c0, c1;
+    bool in0, in1, lo0 = false, lo1 = false, hi0 = false, hi1 = false;
+    if (CLAMP) {        // lo < hi on this path (see bwd_elem)
+        lo0 = x0 < q.lo; hi0 = x0 > q.hi;
+        lo1 = x1 < q.lo; hi1 = x1 > q.hi;
+        c0 = hi0 ? q.hi : (lo0 ? q.lo : x0);
+        c1 = hi1 ? q.hi : (lo1 ? q.lo : x1);
+        in0 = (c0 == x0); in1 = (c1 == x1);
+    } else {
+        c0 = x0; c1 = x1;
+        in0 = (x0 == x0); in1 = (x1 == x1);
+    }
+    const f32x2 go = pk2(go0, go1);
+    const f32x2 u = add2(pk2(c0, c1), pc.zpn);
+    const f32x2 v = div2_quot(u, pc.d);
+    float v0, v1;
+    upk2(v, v0, v1);
+    const f32x2 e = sub2(pk2(rintf(v0), rintf(v1)), v);
+    const f32x2 code = add2(v, e);
+    const f32x2 gn = mul2(go, pc.d.sn);                  // -g
+    const f32x2 r = fma2(go, pc.d.s, gn);                // go*s - g, exact
+    const f32x2 gu = fma2(r, pc.d.yn, go);               // RN(g / s)
+    float gu0, gu1;
+    upk2(gu, gu0, gu1);
+    o0 = in0 ? gu0 : 0.f;
+    o1 = in1 ? gu1 : 0.f;
+    const f32x2 t2n = mul2_rounded(gn, div2_quot(v, pc.d));       // -fl(g * fl(v/s))
+    a2.se = add2(a2.se, add2(mul2_rounded(go, code), t2n));       // fl(go*code) - fl(g*fl(v/s))
+    a2.sz = add2(a2.sz, sub2(go, gu));
+    if (METHOD == MHAQ_FQ_LSQ) {
+        a2.sn = fma2(gn, e, a2.sn);                      // -(g*e)
+    } else if (NOISE == NOISE_EXPLICIT) {
+        a2.sn = add2(a2.sn, mul2_rounded(mul2(gn, pc.c), pk2(rn0, rn1)));   // -fl(fl(c*g)*r)
+    } else {
+        float t0, t1;
+        upk2(mul2(gn, pc.c), t0, t1);                    // -fl(c*g)
+        t0 = __uint_as_float(__float_as_uint(t0) ^ (sf0 & 0x80000000u));
+        t1 = __uint_as_float(__float_as_uint(t1) ^ (sf1 & 0x80000000u));
+        a2.sn = fma2(pk2(t0, t1), pc.half, a2.sn);       // -(c*g)*r,  r = bit - 0.5
+    }
+    if (CLAMP) {
+        if (lo0) acc.sl += gu0;
+        if (lo1) acc.sl += gu1;
+        if (hi0) acc.sh += gu0;
+        if (hi1) acc.sh += gu1;
+    }
+}
+
 // Guard fall-back of the fast path (rare: tiny non-zero / huge gradients): recompute the
 // input gradient of one 16-element thread batch with true IEEE divisions, RE-LOADING the
 // operands (L2 hits) so that nothing of this path stays live in the streaming loop, and
@@ -498,6 +573,12 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
         const float *rr = (NOISE == NOISE_EXPLICIT) ? r + k.row_off : nullptr;
         float *gxr = gx ? gx + k.row_off : nullptr;
         Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f};
+        Acc2 a2 = {0ull, 0ull, 0ull};
+        PairConst pc;
+        pc.d = make_div2(q.s, bc.rcp);
+        pc.zpn = bc2(-q.zp);
+        pc.c = bc2(kInvSqrt3);
+        pc.half = bc2(0.5f);
         uint4 rnd = make_uint4(0, 0, 0, 0);
         int64_t curT = -1;
 
@@ -547,10 +628,17 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
                         constexpr int kTop = 31;
                         const int sh = (b * kU + u) * 4;     // compile-time after unrolling
                         float4 o;
-                        o.x = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].x, gv[u].x, rv4[u].x, nw << (kTop - sh - 0), q, bc, acc);
-                        o.y = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].y, gv[u].y, rv4[u].y, nw << (kTop - sh - 1), q, bc, acc);
-                        o.z = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].z, gv[u].z, rv4[u].z, nw << (kTop - sh - 2), q, bc, acc);
-                        o.w = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].w, gv[u].w, rv4[u].w, nw << (kTop - sh - 3), q, bc, acc);
+                        if (kProductDiv && !CODEGRAD) {
+                            bwd_pair_fast<METHOD, CLAMP, NOISE>(xv[u].x, xv[u].y, gv[u].x, gv[u].y, rv4[u].x, rv4[u].y,
+                                                                nw << (kTop - sh - 0), nw << (kTop - sh - 1), q, pc, a2, acc, o.x, o.y);
+                            bwd_pair_fast<METHOD, CLAMP, NOISE>(xv[u].z, xv[u].w, gv[u].z, gv[u].w, rv4[u].z, rv4[u].w,
+                                                                nw << (kTop - sh - 2), nw << (kTop - sh - 3), q, pc, a2, acc, o.z, o.w);
+                        } else {
+                            o.x = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].x, gv[u].x, rv4[u].x, nw << (kTop - sh - 0), q, bc, acc);
+                            o.y = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].y, gv[u].y, rv4[u].y, nw << (kTop - sh - 1), q, bc, acc);
+                            o.z = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].z, gv[u].z, rv4[u].z, nw << (kTop - sh - 2), q, bc, acc);
+                            o.w = bwd_elem<METHOD, CLAMP, NOISE, true, CODEGRAD>(xv[u].w, gv[u].w, rv4[u].w, nw << (kTop - sh - 3), q, bc, acc);
+                        }
                         if (gxr) st_stream4(gxr + p, o);
                     }
                     if (odd && gxr)   // rare: exact IEEE division for the input gradient
@@ -588,6 +676,12 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
                     if (gxr) store4<VEC>(gxr, p, g.n_inner, o);
                 }
             }
+        }
+        if (kProductDiv && !CODEGRAD) {   // fold the packed lanes (fixed order) into the record
+            float l, h;
+            upk2(a2.se, l, h); acc.se += l + h;
+            upk2(a2.sn, l, h); acc.sn -= l + h;          // accumulated with the opposite sign
+            upk2(a2.sz, l, h); acc.sz += l + h;
         }
         flush_record<CLAMP>(acc, t, ws);
     }
