@@ -261,6 +261,7 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
             if tot > 0:
                 res["fake_quant_kernel_share"] = round(fq / tot, 4)
                 res["fake_quant_ms_per_step"] = round(fq / 2 / 1e3, 3)
+                res["gpu_kernel_ms_per_step"] = round(tot / 2 / 1e3, 2)   # rest of the step = GPU idle
         except Exception as exc:   # profiler unavailable: the throughput numbers stand alone
             res["fake_quant_kernel_share"] = None
             res["profiler_error"] = str(exc)[:80]

@@ -366,3 +366,76 @@ def row_stats(x2d: torch.Tensor):
     check(lib.mhaq_fq_rowstat_f32(_ptr(x2d), rows, inner, _ptr(o[0]), _ptr(o[1]), _ptr(o[2]),
                                   _ptr(o[3]), _stream()), "mhaq_fq_rowstat_f32")
     return o[0], o[1], o[2], o[3]
+
+
+def row_stats_backward(gx, x2d, row_min=None, n_at_min=None, g_min=None, row_max=None,
+                       n_at_max=None, g_max=None):
+    """gx + amin/amax backward in one pass: adds g_min[row]/n_at_min[row] to every element equal
+    to the row minimum (torch's even split among ties) and likewise for the maximum."""
+    _require_cuda(x2d)
+    x2d = x2d.contiguous()
+    rows, inner = x2d.shape
+    out = torch.empty_like(x2d)
+    c = lambda t: None if t is None else t.contiguous()
+    gx, row_min, n_at_min, g_min, row_max, n_at_max, g_max = map(
+        c, (gx, row_min, n_at_min, g_min, row_max, n_at_max, g_max))
+    check(lib.mhaq_fq_rowstat_bwd_f32(_ptr(gx), _ptr(x2d), rows, inner, _ptr(row_min), _ptr(n_at_min),
+                                      _ptr(g_min), _ptr(row_max), _ptr(n_at_max), _ptr(g_max),
+                                      _ptr(out), _stream()), "mhaq_fq_rowstat_bwd_f32")
+    return out
+
+
+class _WeightFakeQuantFn(torch.autograd.Function):
+    """Per-channel weight quantizer with the zero point fused in:
+        zp = row minimum of the weight (gdnsq_conv2d.py:80-81), wq = fake_quant(w, s, zp)
+    Outputs (wq, row_min, row_max): the row range is what ModelHelper.get_model_values
+    (model_helper.py:24-25) needs, so the weight is reduced ONCE per step instead of three
+    times, and the three amin/amax backward passes (even split among ties) collapse into one
+    scatter fused with the input gradient."""
+
+    @staticmethod
+    def forward(ctx, w, scale, method, noise, philox):
+        ctx.set_materialize_grads(False)
+        w = w.contiguous()
+        rows = w.shape[0]
+        w2 = w.view(rows, -1)
+        mn, mx, cmn, cmx = row_stats(w2)
+        pshape = (rows,) + (1,) * (w.dim() - 1)
+        L = _Launch(w, scale, mn.view(pshape), None, None)
+        wq, _, _ = _forward_impl(w, L, True, False, False)
+        ctx.save_for_backward(w, scale, mn, mx, cmn, cmx)
+        ctx.method, ctx.noise, ctx.philox, ctx.pshape = method, noise, philox, pshape
+        return wq, mn, mx
+
+    @staticmethod
+    def backward(ctx, g_wq, g_mn, g_mx):
+        w, scale, mn, mx, cmn, cmx = ctx.saved_tensors
+        rows = w.shape[0]
+        w2 = w.view(rows, -1)
+        g_scale = None
+        if g_wq is not None:
+            L = _Launch(w, scale, mn.view(ctx.pshape), None, None)
+            gx, out = _backward_impl(g_wq, w, L, ctx.method, False, ctx.noise, True, ctx.philox)
+            g_scale = _reduce_to_param(out[0], scale, L.geo, w.shape)
+            g_min = out[1] if g_mn is None else out[1] + g_mn
+            gx2 = gx.view(rows, -1)
+        else:
+            gx2, g_min = None, g_mn
+        if not ctx.needs_input_grad[0]:
+            return None, g_scale, None, None, None
+        if g_min is None and g_mx is None:
+            gw = torch.zeros_like(w) if gx2 is None else gx2.view_as(w)
+        else:
+            gw = row_stats_backward(gx2, w2, mn if g_min is not None else None,
+                                    cmn if g_min is not None else None, g_min,
+                                    mx if g_mx is not None else None,
+                                    cmx if g_mx is not None else None, g_mx).view_as(w)
+        return gw, (g_scale if ctx.needs_input_grad[1] else None), None, None, None
+
+
+def weight_fake_quant(w, scale, method="STE", noise=None, philox=None):
+    """(wq, row_min, row_max) for a per-channel weight (channel = dim 0); see _WeightFakeQuantFn."""
+    _require_cuda(w)
+    if scale.numel() != w.shape[0]:
+        raise RuntimeError("weight_fake_quant expects one scale per output channel (dim 0)")
+    return _WeightFakeQuantFn.apply(w, scale, _method_id(method), noise, philox)

@@ -136,6 +136,14 @@ class Quantizer:
         return ops.fake_quant(value, self.scale, self._zp_like(value), self.min_val, self.max_val,
                               method=self._method(), noise=noise)
 
+    def fake_quant_weight(self, weight, noise=None):
+        """Per-channel weight path with the row-minimum zero point computed in the same
+        pass (reads self.scale; sets self.zero_point like NoisyConv2d.forward does,
+        gdnsq_conv2d.py:80-84).  Returns (weight_q, row_min, row_max)."""
+        wq, mn, mx = ops.weight_fake_quant(weight, self.scale, method=self._method(), noise=noise)
+        self.zero_point = mn.view((weight.shape[0],) + (1,) * (weight.dim() - 1))
+        return wq, mn, mx
+
     def fake_quant_eval(self, value):
         """No-grad fused forward that also yields (min code, max code, #non-finite) — the
         eval extras of gdnsq.py:211-217 / gdnsq_act.py:51-54 without extra passes."""

@@ -44,17 +44,35 @@ class NoisyConv2d(nn.Conv2d):
 
     def quantized_weight(self):
         """(weight_q, bias_q) — computed once per parameter version (see _wcache)."""
+        w, b, _, _ = self._quantize()
+        return w, b
+
+    def row_range(self):
+        """(row_min, row_max) of the weight, differentiable, from the same pass that produced
+        the quantized weight (consumed by ModelHelper.get_model_values); None per-tensor."""
+        _, _, mn, mx = self._quantize()
+        return (mn, mx) if mn is not None else None
+
+    def _quantize(self):
         key, hit = self._wq_cache.lookup((self.weight, self.log_wght_s, self.bias),
                                          torch.is_grad_enabled(), self.training)
         if hit is not None:
             return hit
         s = torch.exp2(self.log_wght_s)
         self.Q.scale = s
-        if self.qscheme == QScheme.PER_CHANNEL:
-            mn = self.weight.amin((1, 2, 3), keepdim=True)
-        elif self.qscheme == QScheme.PER_TENSOR:
-            mn = self.weight.amin()
-        self.Q.zero_point = mn
+        mx = None
+        if self.qscheme == QScheme.PER_CHANNEL and self.positive_scale_ok():
+            # fused: row min (zero point) + row max in one pass, quantization in the next
+            weight, mn_flat, mx = self.Q.fake_quant_weight(self.weight)
+            mn = self.Q.zero_point
+        else:
+            if self.qscheme == QScheme.PER_CHANNEL:
+                mn = self.weight.amin((1, 2, 3), keepdim=True)
+            else:
+                mn = self.weight.amin()
+            self.Q.zero_point = mn
+            mn_flat = None
+            weight = self.Q.fake_quant(self.weight)
 
         if self.quant_bias:
             self.Q_b.scale = s.ravel()
@@ -62,12 +80,15 @@ class NoisyConv2d(nn.Conv2d):
             bias = self.Q_b.fake_quant(self.bias)
         else:
             bias = self.bias
-        weight = self.Q.fake_quant(self.weight)
-        # the cache holds the weight only; a quantized bias (tiny) is recomputed per call
-        # so that one cache entry never pins two autograd graphs
+        out = (weight, bias, mn_flat, mx)
+        # a quantized bias (tiny) is recomputed per call so that one cache entry never pins
+        # two autograd graphs
         if not self.quant_bias:
-            self._wq_cache.store(key, (weight, bias))
-        return weight, bias
+            self._wq_cache.store(key, out)
+        return out
+
+    def positive_scale_ok(self):
+        return self.Q.positive_scale and self.weight.is_cuda
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         weight, bias = self.quantized_weight()

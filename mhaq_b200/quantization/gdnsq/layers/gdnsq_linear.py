@@ -36,21 +36,31 @@ class NoisyLinear(nn.Linear):
         self._wq_cache = WeightQuantCache()
 
     def quantized_weight(self):
+        return self._quantize()[0]
+
+    def row_range(self):
+        """(row_min, row_max), differentiable, from the quantization pass; None per-tensor."""
+        _, mn, mx = self._quantize()
+        return (mn, mx) if mn is not None else None
+
+    def _quantize(self):
         key, hit = self._wq_cache.lookup((self.weight, self.log_wght_s), torch.is_grad_enabled(),
                                          self.training)
         if hit is not None:
             return hit
         if self.qscheme == QScheme.PER_CHANNEL:
-            s = torch.exp2(self.log_wght_s).reshape(self.out_features, 1)
-            mn = self.weight.amin(1, keepdim=True)
+            self.Q.scale = torch.exp2(self.log_wght_s).reshape(self.out_features, 1)
+            if self.Q.positive_scale and self.weight.is_cuda:
+                out = self.Q.fake_quant_weight(self.weight)
+            else:
+                self.Q.zero_point = self.weight.amin(1, keepdim=True)
+                out = (self.Q.fake_quant(self.weight), None, None)
         else:
-            s = torch.exp2(self.log_wght_s)
-            mn = self.weight.amin()
-        self.Q.scale = s
-        self.Q.zero_point = mn
-        weight = self.Q.fake_quant(self.weight)
-        self._wq_cache.store(key, weight)
-        return weight
+            self.Q.scale = torch.exp2(self.log_wght_s)
+            self.Q.zero_point = self.weight.amin()
+            out = (self.Q.fake_quant(self.weight), None, None)
+        self._wq_cache.store(key, out)
+        return out
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         return F.linear(input, self.quantized_weight(), self.bias)

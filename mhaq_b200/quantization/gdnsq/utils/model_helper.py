@@ -22,7 +22,11 @@ class ModelHelper:
                 if qscheme == QScheme.PER_CHANNEL:
                     dims = tuple(range(1, m.weight.dim()))
                     log_wght_s.append(m.log_wght_s.ravel())
-                    mn, mx = m.weight.amin(dims), m.weight.amax(dims)
+                    # the layer already reduced the weight rows in this step's forward (fused
+                    # row-stat kernel); reuse its differentiable (min, max) instead of two more
+                    # passes over the weight
+                    rr = m.row_range() if hasattr(m, "row_range") and m.weight.is_cuda else None
+                    mn, mx = rr if rr is not None else (m.weight.amin(dims), m.weight.amax(dims))
                 else:
                     log_wght_s.append(m.log_wght_s)
                     mn, mx = m.weight.amin(), m.weight.amax()

@@ -150,3 +150,38 @@ def test_resnet20_qat_steps_run_and_learnable_params_get_grads():
             q.validation_step((x, t), 0)
         assert "Actual activations max bit widths" in q.logged
         assert float(q.logged["Actual weights max bit width"]) <= 10.01   # calibrated to 10 bits
+
+
+def test_model_helper_reuses_row_stats_and_matches_torch_autograd():
+    """The fused weight path (row min/max shared with ModelHelper) must give the same loss
+    gradients as plain torch amin/amax on the same weights."""
+    from mhaq_b200.aux.types import QScheme
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_act import NoisyAct
+    from mhaq_b200.quantization.gdnsq.utils.model_helper import ModelHelper
+    torch.manual_seed(3)
+    conv = NoisyConv2d(8, 16, 3, padding=1, bias=False, qscheme=QScheme.PER_CHANNEL,
+                       qnmethod=QNMethod.LSQ).cuda()
+    with torch.no_grad():
+        conv.log_wght_s.fill_(-4.0)
+        conv.weight[0, 0, 0, 0] = conv.weight[0].min()    # tie
+    model = nn.Sequential(NoisyAct(signed=True).cuda(), conv)
+    conv.train()
+    wq, _ = conv.quantized_weight()
+    las, laq, lws, lwq = ModelHelper.get_model_values(model, QScheme.PER_CHANNEL)
+    assert conv._wq_cache.hits >= 1, "ModelHelper must reuse the layer's row statistics"
+    go = torch.randn_like(wq)
+    coef = torch.randn_like(lwq)
+    ((wq * go).sum() + (lwq * coef).sum() + (lws * 0.3).sum()).backward()
+    # reference computation with the oracle + torch amin/amax
+    w = conv.weight.detach().cpu().clone().requires_grad_(True)
+    ls = conv.log_wght_s.detach().cpu().clone().requires_grad_(True)
+    wo = O.weight_fake_quant(w, ls, True, "LSQ")
+    mn, mx = w.amin((1, 2, 3)), w.amax((1, 2, 3))
+    lwq_o = torch.log2(mx - mn + torch.exp2(ls.ravel()))
+    ((wo * go.cpu()).sum() + (lwq_o * coef.cpu()).sum() + (ls.ravel() * 0.3).sum()).backward()
+    assert_bit_exact(wq, wo, "wq")
+    assert_close_rel(lwq, lwq_o, 1e-6, "log_w range")
+    assert_close_rel(conv.weight.grad, w.grad, 1e-5, "g_weight", abs_floor=2e-5)
+    assert_close_rel(conv.log_wght_s.grad, ls.grad, 1e-5, "g_log_wght_s", abs_floor=5e-5)

@@ -355,3 +355,32 @@ def test_full_size_vs_oracle_on_device(fq, log2n, bits):
     y2 = fq.fake_quant(xs, s, b, b, hi, method="STE", philox=(3, 4))
     y2.backward(go * 4.0)
     assert torch.equal(xs.grad, gx_g * 4.0)
+
+
+# ---------------------------------------------------------------------------
+# row statistics (amin / amax with tie counts) and their backward
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,inner", [(64, 576), (32, 450), (7, 4608), (3, 10), (1, 100000)])
+def test_rowstat_matches_torch_amin_amax_and_backward(fq, rows, inner):
+    from mhaq_b200 import ops
+    torch.manual_seed(rows * 1000 + inner)
+    w = torch.randn(rows, inner)
+    w[0, 3] = w[0].min()          # ties for the minimum
+    w[0, 5] = w[0].min()
+    w[rows - 1, 1] = w[rows - 1].max()    # tie for the maximum
+    wg = w.cuda()
+    mn, mx, cmn, cmx = ops.row_stats(wg)
+    assert torch.equal(mn.cpu(), w.amin(1)) and torch.equal(mx.cpu(), w.amax(1))
+    assert torch.equal(cmn.cpu(), (w == w.amin(1, keepdim=True)).sum(1).float())
+    assert torch.equal(cmx.cpu(), (w == w.amax(1, keepdim=True)).sum(1).float())
+    # backward: torch's amin/amax split the gradient evenly among ties
+    gmn, gmx = torch.randn(rows), torch.randn(rows)
+    gx = torch.randn(rows, inner)
+    wr = w.clone().requires_grad_(True)
+    ((wr.amin(1) * gmn).sum() + (wr.amax(1) * gmx).sum() + (wr * gx).sum()).backward()
+    out = ops.row_stats_backward(gx.cuda(), wg, mn, cmn, gmn.cuda(), mx, cmx, gmx.cuda())
+    H.assert_close_rel(out, wr.grad, 1e-6, "rowstat backward", abs_floor=1e-7)
+    out2 = ops.row_stats_backward(gx.cuda(), wg, mn, cmn, gmn.cuda())
+    wr.grad = None
+    ((wr.amin(1) * gmn).sum() + (wr * gx).sum()).backward()
+    H.assert_close_rel(out2, wr.grad, 1e-6, "rowstat backward (min only)", abs_floor=1e-7)
