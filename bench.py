@@ -50,6 +50,11 @@ def parse_args():
     ap.add_argument("--no-resnet", action="store_true", help="skip the ResNet-18 W4A4 QAT leg")
     ap.add_argument("--resnet-batch", type=int, default=256, help="per-GPU batch (config 4)")
     ap.add_argument("--resnet-steps", type=int, default=12)
+    ap.add_argument("--qat-model", default="resnet18", choices=["resnet18", "resnet20"],
+                    help="resnet18 = configs[3] (ImageNet-shaped, STE W4A4); resnet20 = configs[2] "
+                         "(CIFAR-100-shaped; use --qat-method AEWGS --qat-bits 1)")
+    ap.add_argument("--qat-method", default="STE", choices=["STE", "LSQ", "AEWGS", "EWGS"])
+    ap.add_argument("--qat-bits", type=int, default=4)
     ap.add_argument("--no-eager-ref", action="store_true",
                     help="skip timing the reference's ATen chain on the GPU (second denominator)")
     return ap.parse_args()
@@ -208,9 +213,11 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     torch.set_float32_matmul_precision("high")
     B = a.resnet_batch
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.randn(B, 3, 224, 224, device=dev, generator=g)
-    t = torch.randint(0, 1000, (B,), device=dev, generator=g)
-    q = harness.build_qat("resnet18", dev, qnmethod="STE", act_bit=4, weight_bit=4, distillation=True,
+    side, classes = (224, 1000) if a.qat_model == "resnet18" else (32, 100)
+    x = torch.randn(B, 3, side, side, device=dev, generator=g)
+    t = torch.randint(0, classes, (B,), device=dev, generator=g)
+    q = harness.build_qat(a.qat_model, dev, qnmethod=a.qat_method, act_bit=a.qat_bits,
+                          weight_bit=a.qat_bits, distillation=True, num_classes=classes,
                           calib_batch=x[: min(B, 64)])
     if use_dist:
         from torch.nn.parallel import DistributedDataParallel as DDP
@@ -241,11 +248,12 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     k = a.resnet_steps
     ms = time_region(step, k, use_dist) / k
     ms_e = time_region(step_e2e, max(3, k // 2), use_dist) / max(3, k // 2)
-    res = {"workload": "configs[3] ResNet-18 224x224 STE W4A4 QAT, distillation, RAdam, fp32/TF32, "
+    cfg = "configs[3] ResNet-18 224x224" if a.qat_model == "resnet18" else "configs[2] ResNet-20 32x32 (CIFAR-100 shaped)"
+    res = {"workload": f"{cfg} {a.qat_method} W{a.qat_bits}A{a.qat_bits} QAT, distillation, RAdam, fp32/TF32, "
                        f"batch {B}/GPU, {'DDP dp%d' % world if use_dist else 'single GPU'}",
            "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
            "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1), "n_gpus": world,
-           "quantized_act_elems_per_step": 1680896 * B}
+           "quantized_act_elems_per_step": (1680896 if a.qat_model == "resnet18" else 184320) * B}
     if rank == 0 and not use_dist and profile_share:   # (a rank-local DDP step would dead-lock the other ranks)
         try:   # share of the step spent in the fake-quant kernels (CUPTI kernel times)
             from torch.profiler import profile, ProfilerActivity
@@ -418,7 +426,8 @@ def run_ours(a):
     if not a.no_resnet:
         rn = resnet18_leg(a, dev, world, rank, use_dist)
         if rank == 0:
-            out["resnet18_w4a4_qat"] = rn
+            out["resnet18_w4a4_qat" if (a.qat_model, a.qat_method, a.qat_bits) == ("resnet18", "STE", 4)
+                else f"{a.qat_model}_{a.qat_method.lower()}_w{a.qat_bits}a{a.qat_bits}_qat"] = rn
     if rank == 0:
         if not a.no_eager_ref:
             out["reference_eager_gpu"] = eager_reference_leg(a, dev)

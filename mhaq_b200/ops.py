@@ -288,27 +288,31 @@ class _FakeQuantFn(torch.autograd.Function):
         L = _Launch(x, scale, zp, lo, hi)
         y, codes, _ = _forward_impl(x, L, want_y=not code_only, want_codes=code_only,
                                     want_minmax=False)
-        ctx.save_for_backward(x, *(p for p in (scale, zp, lo, hi) if torch.is_tensor(p)))
-        ctx.meta = (tuple(torch.is_tensor(p) for p in (scale, zp, lo, hi)),
-                    tuple(None if torch.is_tensor(p) else p for p in (scale, zp, lo, hi)))
+        prm = (scale, zp, lo, hi)
+        ctx.save_for_backward(x, *(p for p in prm if torch.is_tensor(p)))
+        ctx.is_t = tuple(torch.is_tensor(p) for p in prm)
+        # the flattened parameter views of L alias the saved tensors' storage: reuse the launch
+        # description in backward instead of re-deriving it (host overhead matters for the
+        # small tensors of CIFAR-sized models)
+        ctx.L = L
         ctx.method, ctx.noise, ctx.philox, ctx.code_only = method, noise, philox, code_only
         return codes if code_only else y
 
     @staticmethod
     def backward(ctx, go):
-        saved = list(ctx.saved_tensors)
-        x = saved.pop(0)
-        is_t, consts = ctx.meta
-        prm = [saved.pop(0) if t else c for t, c in zip(is_t, consts)]
-        scale, zp, lo, hi = prm
-        L = _Launch(x, scale, zp, lo, hi)
+        saved = ctx.saved_tensors          # also performs autograd's in-place-modification check
+        x = saved[0]
+        L = ctx.L
         need = ctx.needs_input_grad
         gx, out = _backward_impl(go, x, L, ctx.method, ctx.code_only, ctx.noise, need[0], ctx.philox)
         geo = L.geo
         grads = [gx if need[0] else None]
-        for i, p in enumerate(prm):
-            if is_t[i] and need[1 + i]:
-                grads.append(_reduce_to_param(out[i], p, geo, x.shape))
+        k = 1
+        for i, is_t in enumerate(ctx.is_t):
+            if is_t:
+                p = saved[k]
+                k += 1
+                grads.append(_reduce_to_param(out[i], p, geo, x.shape) if need[1 + i] else None)
             else:
                 grads.append(None)
         return (*grads, None, None, None, None)
