@@ -148,42 +148,24 @@ EXCLUDED = {"resnet18": ("conv1", "fc"), "resnet20": ("conv1", "linear")}
 # ------------------------------------------------------------------ calibration
 @torch.no_grad()
 def calibrate(qmodel: LModule, batch, act_bits=10, weight_bits=10):
-    """Effect of Trainer.calibrate on one batch: weights get
-    log_wght_s = max(log_wght_s, log2((max-min)/(2^bits-1))) per channel
-    (minmaxobserver.py:69-88); every NoisyAct gets act_b=min, log_act_s=log2(range/(2^bits-1)),
-    log_act_q=log_act_s+bits from the min/max of its input (minmaxobserver.py:39-66),
-    zero-range activations are frozen ("pruned")."""
+    """`Trainer.calibrate` (training/trainer.py:187-223) on one batch: weight scales via
+    apply_quantile_weights_s, activation ranges via MinMaxObserver forward hooks on every
+    NoisyAct during an eval forward, then apply_mean_stats_activations."""
+    from .quantization.gdnsq.calib.hooks import register_lightning_activation_forward_hook
+    from .quantization.gdnsq.calib.minmaxobserver import (MinMaxObserver, apply_mean_stats_activations,
+                                                          apply_quantile_weights_s)
     model = qmodel.model
-    for m in model.modules():
-        if isinstance(m, (NoisyConv2d, NoisyLinear)):
-            w = m.weight.detach()
-            if m.log_wght_s.numel() > 1:
-                flat = w.reshape(w.shape[0], -1)
-                rng = (flat.amax(1) - flat.amin(1)).reshape(m.log_wght_s.shape)
-            else:
-                rng = (w.max() - w.min()).reshape(m.log_wght_s.shape)
-            m.log_wght_s.data = torch.max(m.log_wght_s.data, torch.log2(rng / (2 ** weight_bits - 1)))
-    stats, hooks = {}, []
-    for m in model.modules():
-        if isinstance(m, NoisyAct):
-            hooks.append(m.register_forward_hook(
-                lambda mod, inp, out: stats.__setitem__(mod, (inp[0].min(), inp[0].max()))))
-    was_training = model.training
-    model.eval()
-    model(batch)
-    model.train(was_training)
-    for h in hooks:
-        h.remove()
-    for m, (mn, mx) in stats.items():
-        if float(mx - mn) > 0:
-            log_s = torch.log2((mx - mn) / (2 ** act_bits - 1))
-            m.act_b.data.fill_(float(mn))
-            m.log_act_s.data.fill_(float(log_s))
-            m.log_act_q.data.fill_(float(log_s) + act_bits)
-        else:
-            for p in (m.log_act_q, m.log_act_s, m.act_b):
-                p.requires_grad_(False)
-            m.log_act_q.data.zero_(); m.log_act_s.data.zero_(); m.act_b.data.fill_(float(mn))
+    if weight_bits:
+        apply_quantile_weights_s(model, wbits=weight_bits)
+    if act_bits:
+        handles = register_lightning_activation_forward_hook(model, MinMaxObserver())
+        was_training = model.training
+        model.eval()
+        model(batch)
+        model.train(was_training)
+        for h in handles:
+            h.remove()
+        apply_mean_stats_activations(model, abits=act_bits)
 
 
 # ------------------------------------------------------------------ build + fit

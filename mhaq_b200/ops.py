@@ -38,7 +38,9 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    # raw cudaStream_t of torch's current stream; ~50x cheaper than torch.cuda.current_stream()
+    # (which builds a Stream object) — this is called for every kernel launch
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def _require_cuda(x: torch.Tensor) -> None:
@@ -115,8 +117,10 @@ def _prep_param(p, x: torch.Tensor, name: str):
         p = p.to(x.device)
     if p.dtype != torch.float32:
         p = p.float()
-    flat = p.detach().contiguous().reshape(-1)
-    return flat, (0 if flat.numel() == 1 else 1)
+    if not p.is_contiguous():
+        p = p.contiguous()
+    # only the data pointer and the element count are used: no detach / reshape views needed
+    return p, (0 if p.numel() == 1 else 1)
 
 
 def _workspace(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
@@ -132,7 +136,7 @@ _ticket_bufs = {}
 
 def _tickets(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
     need = lib.mhaq_fq_ticket_count(geo.n_rows, geo.n_inner, geo.n_ch)
-    key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+    key = (x.device.index, torch._C._cuda_getCurrentRawStream(x.device.index))
     buf = _ticket_bufs.get(key)
     if buf is None or buf.numel() < need:
         n = max(4096, 1 << (int(need) - 1).bit_length())

@@ -89,3 +89,31 @@ def test_cpu_forward_fails_loudly():
     act = NoisyAct()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         act(torch.randn(4, 4))
+
+
+def test_calibration_api_rebinds_parameters_like_the_reference():
+    from mhaq_b200.quantization.gdnsq.calib.minmaxobserver import (MinMaxObserver, apply_mean_stats_activations,
+                                                                   apply_quantile_weights_s)
+    q = _quantized("resnet20")
+    conv = q.model.layer1[0].conv1[1] if False else q.model.layer1[0].conv1._modules["0"]
+    act = q.model.layer1[0].conv1.activations_quantizer
+    old_ws, old_as = conv.log_wght_s, act.log_act_s
+    apply_quantile_weights_s(q.model, wbits=10)
+    assert conv.log_wght_s is not old_ws and conv.log_wght_s.requires_grad
+    w = conv.weight.detach()
+    expect = torch.log2((w.amax((1, 2, 3)) - w.amin((1, 2, 3))) / (2 ** 10 - 1)).reshape(-1, 1, 1, 1)
+    assert torch.allclose(conv.log_wght_s.detach(), torch.max(torch.full_like(expect, -12.0), expect))
+    obs = MinMaxObserver()
+    x1, x2 = torch.randn(2, 16, 8, 8), torch.randn(2, 16, 8, 8) * 3
+    for m in q.model.modules():
+        if isinstance(m, NoisyAct):
+            obs(m, (x1,), None)
+            obs(m, (x2,), None)
+    apply_mean_stats_activations(q.model, abits=10)
+    mn, mx = torch.minimum(x1.min(), x2.min()), torch.maximum(x1.max(), x2.max())
+    assert act.log_act_s is not old_as
+    assert torch.allclose(act.act_b.detach(), mn.reshape(1))
+    log_s = torch.log2((mx - mn) / (2 ** 10 - 1))
+    assert torch.allclose(act.log_act_s.detach(), log_s.reshape(1))
+    assert torch.allclose(act.log_act_q.detach(), (log_s + 10).reshape(1))
+    assert act.act_b.requires_grad and act.log_act_s.requires_grad
