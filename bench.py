@@ -55,6 +55,8 @@ def parse_args():
                          "(CIFAR-100-shaped; use --qat-method AEWGS --qat-bits 1)")
     ap.add_argument("--qat-method", default="STE", choices=["STE", "LSQ", "AEWGS", "EWGS"])
     ap.add_argument("--qat-bits", type=int, default=4)
+    ap.add_argument("--graph", action="store_true",
+                    help="QAT leg: capture the whole training step in a CUDA graph (single GPU)")
     ap.add_argument("--no-eager-ref", action="store_true",
                     help="skip timing the reference's ATen chain on the GPU (second denominator)")
     return ap.parse_args()
@@ -223,12 +225,19 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
         from torch.nn.parallel import DistributedDataParallel as DDP
         q.model = DDP(q.model, device_ids=[dev.index], find_unused_parameters=True,
                       gradient_as_bucket_view=True)
-    opt = q.configure_optimizers()
+    graphed = None
+    if a.graph and not use_dist:
+        graphed = harness.GraphedTrainStep(q, (x, t), seed=1234)
+        opt = graphed.opt
+    else:
+        opt = q.configure_optimizers()
     q.train(); q.wrapped_criterion.train(); q.tmodel.eval()
     hx = x.cpu().pin_memory(); ht = t.cpu().pin_memory()
     hloss = torch.empty((), dtype=torch.float32).pin_memory()
 
     def step():
+        if graphed is not None:
+            return graphed()
         loss = q.training_step((x, t), 0)
         loss.backward()
         opt.step()
@@ -236,6 +245,9 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
         return loss
 
     def step_e2e():
+        if graphed is not None:
+            hloss.copy_(graphed((hx, ht)), non_blocking=True)
+            return
         xd = hx.to(dev, non_blocking=True); td = ht.to(dev, non_blocking=True)
         loss = q.training_step((xd, td), 0)
         loss.backward()
@@ -250,11 +262,12 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     ms_e = time_region(step_e2e, max(3, k // 2), use_dist) / max(3, k // 2)
     cfg = "configs[3] ResNet-18 224x224" if a.qat_model == "resnet18" else "configs[2] ResNet-20 32x32 (CIFAR-100 shaped)"
     res = {"workload": f"{cfg} {a.qat_method} W{a.qat_bits}A{a.qat_bits} QAT, distillation, RAdam, fp32/TF32, "
-                       f"batch {B}/GPU, {'DDP dp%d' % world if use_dist else 'single GPU'}",
+                       f"batch {B}/GPU, {'DDP dp%d' % world if use_dist else 'single GPU'}"
+                       f"{', whole step replayed from a CUDA graph' if graphed is not None else ''}",
            "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
            "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1), "n_gpus": world,
            "quantized_act_elems_per_step": (1680896 if a.qat_model == "resnet18" else 184320) * B}
-    if rank == 0 and not use_dist and profile_share:   # (a rank-local DDP step would dead-lock the other ranks)
+    if rank == 0 and not use_dist and profile_share and graphed is None:   # (a rank-local DDP step would dead-lock the other ranks)
         try:   # share of the step spent in the fake-quant kernels (CUPTI kernel times)
             from torch.profiler import profile, ProfilerActivity
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -273,7 +286,9 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
         except Exception as exc:   # profiler unavailable: the throughput numbers stand alone
             res["fake_quant_kernel_share"] = None
             res["profiler_error"] = str(exc)[:80]
-    del q, opt
+    if graphed is not None:
+        graphed.close()
+    del q, opt, graphed
     torch.cuda.empty_cache()
     return res
 

@@ -208,3 +208,61 @@ def fit_steps(qmodel: LModule, batches, ddp: bool = False, device=None, on_step=
         if on_step is not None:
             on_step(i, loss)
     return qmodel
+
+
+class GraphedTrainStep:
+    """One QAT training step (teacher + student forward, loss, backward, optimizer) captured
+    in a CUDA graph and replayed — SURVEY.md §8 row (f)-4.  CIFAR-sized models are bound by
+    host launch overhead (ResNet-20, batch 256: ~19 ms of Python/launch time for ~9 ms of GPU
+    work); a replay has none.  Single process / single GPU; the in-kernel noise reads a
+    device-resident Philox state that is advanced inside the graph, so every replay draws
+    fresh noise.  Host-side schedules (`wrapped_criterion.t`, learning-rate callbacks) are
+    frozen at capture time — re-capture after changing them."""
+
+    STRIDE = 4096        # > number of quantizer backward calls per step
+
+    def __init__(self, qmodel: LModule, example_batch, seed: int = 0, warmup: int = 3):
+        from . import ops
+        x, t = example_batch
+        self.ops, self.qmodel = ops, qmodel
+        self.x, self.t = x.clone(), t.clone()
+        dev = x.device
+        self.state = torch.tensor([seed, 0], dtype=torch.int64, device=dev)
+        ops.set_device_philox_state(self.state)
+        params = [p for p in qmodel.parameters() if p.requires_grad]
+        self.opt = qmodel.optimizer(params, lr=torch.tensor(float(qmodel.lr), device=dev),
+                                    capturable=True)
+        qmodel.train()
+        if hasattr(qmodel, "wrapped_criterion"):
+            qmodel.wrapped_criterion.train()
+            qmodel.wrapped_criterion.make_capturable(dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+
+    def _body(self):
+        self.ops.reset_philox_call_counter()
+        self.state[1] += self.STRIDE
+        loss = self.qmodel.training_step((self.x, self.t), 0)
+        loss.backward()
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
+        return loss.detach()
+
+    def __call__(self, batch=None):
+        if batch is not None:
+            self.x.copy_(batch[0], non_blocking=True)
+            self.t.copy_(batch[1], non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    def close(self):
+        self.ops.set_device_philox_state(None)

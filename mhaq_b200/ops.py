@@ -160,13 +160,28 @@ def _next_philox(device: torch.device) -> Tuple[int, int]:
 _philox_dev = {}
 
 
+_philox_call = {}
+
+
 def set_device_philox_state(state: Optional[torch.Tensor]) -> None:
-    """state: int64 CUDA tensor [2] = (seed, step counter) read by the kernels."""
+    """state: int64 CUDA tensor [2] = (seed, stream base) read by the kernels at run time.
+    With a device-resident state nothing host-side changes from step to step, so a training
+    step can be captured in a CUDA graph: advance ``state[1]`` on the device once per step
+    (by at least the number of quantizer backward calls in a step) and call
+    ``reset_philox_call_counter()`` at the start of every step so each backward call gets
+    the same per-call stream index in every (captured or eager) step."""
     if state is None:
         _philox_dev.clear()
+        _philox_call.clear()
         return
     assert state.is_cuda and state.dtype == torch.int64 and state.numel() == 2
     _philox_dev[state.device.index] = state
+    _philox_call[state.device.index] = 0
+
+
+def reset_philox_call_counter() -> None:
+    for k in _philox_call:
+        _philox_call[k] = 0
 
 
 class _Launch:
@@ -268,7 +283,9 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
         else:
             pd = _philox_dev.get(x.device.index)
             if pd is not None:
-                pdev = pd
+                pdev = pd            # kernel: seed = pd[0], offset = pd[1] + this call's index
+                offset = _philox_call[x.device.index]
+                _philox_call[x.device.index] = offset + 1
             else:
                 seed, offset = _next_philox(x.device)
     tk = _tickets(x, geo)

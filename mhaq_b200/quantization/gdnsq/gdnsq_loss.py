@@ -29,9 +29,19 @@ class _PotentialBase(nn.Module):
         self.cnt = 1
         self.t = 0.0
 
+    def make_capturable(self, device):
+        """Keep the running calibration multiplier state (`loss_sum`, `cnt`) in device tensors
+        so that a CUDA-graph replay advances it (a Python int would be frozen at capture)."""
+        self.loss_sum = torch.as_tensor(float(self.loss_sum), dtype=torch.float32, device=device).clone()
+        self.cnt = torch.as_tensor(float(self.cnt), dtype=torch.float32, device=device).clone()
+        # 0-dim CPU constants are legal operands of CUDA ops but their use in backward is a
+        # host->device copy, which a graph capture forbids
+        self.p, self.l_eps, self.r_eps = (t.to(device) for t in (self.p, self.l_eps, self.r_eps))
+        return self
+
     def _combine(self, base_loss, las, laq, lws, lwq):
         self.base_loss = base_loss
-        z = torch.tensor(0)
+        z = torch.zeros((), dtype=torch.int64, device=lws.device)   # == torch.tensor(0), without a host copy
         wloss0 = torch.max(z, (lwq - lws) - (self.wt - self.l_eps)).pow(self.p)
         wloss = wloss0.mean()
         wact = (wloss0 > 0).sum()          # active weight constraints
@@ -46,7 +56,7 @@ class _PotentialBase(nn.Module):
         ploss = calib_mul * l1 * (wmul * wloss + amul * aloss) + l2 * rloss
         if self.training:
             self.loss_sum += rloss.detach()
-            self.cnt += 1
+            self.cnt += 1          # in place when `cnt` is a tensor (see make_capturable)
         self.wloss, self.aloss, self.rloss = wloss, aloss, rloss
         self.s_weight_loss = -lws.mean()
         self.q_weight_loss = lwq.mean()

@@ -185,3 +185,58 @@ def test_model_helper_reuses_row_stats_and_matches_torch_autograd():
     assert_close_rel(lwq, lwq_o, 1e-6, "log_w range")
     assert_close_rel(conv.weight.grad, w.grad, 1e-5, "g_weight", abs_floor=2e-5)
     assert_close_rel(conv.log_wght_s.grad, ls.grad, 1e-5, "g_log_wght_s", abs_floor=5e-5)
+
+
+def test_device_philox_state_matches_by_value_stream():
+    """Kernels reading (seed, base) from device memory must draw the stream (seed, base + call idx)."""
+    import mhaq_b200
+    from mhaq_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(4, 16, 32, 32, device="cuda")
+    go = torch.randn_like(x)
+    s = torch.tensor([0.25], device="cuda"); b = torch.tensor([-2.0], device="cuda")
+    hi = b + 4.0 - s
+
+    def grad_s(**kw):
+        sp = s.clone().requires_grad_(True)
+        y = mhaq_b200.fake_quant(x, sp, b, b, hi, method="STE", **kw)
+        y.backward(go)
+        return sp.grad.clone()
+
+    state = torch.tensor([77, 8192], dtype=torch.int64, device="cuda")
+    ops.set_device_philox_state(state)
+    try:
+        g0 = grad_s()                 # call index 0
+        g1 = grad_s()                 # call index 1
+        ops.reset_philox_call_counter()
+        g0b = grad_s()
+    finally:
+        ops.set_device_philox_state(None)
+    assert torch.equal(g0, grad_s(philox=(77, 8192)))
+    assert torch.equal(g1, grad_s(philox=(77, 8193)))
+    assert torch.equal(g0, g0b) and not torch.equal(g0, g1)
+
+
+def test_cuda_graph_training_step_replays_and_trains():
+    from mhaq_b200 import harness
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    x = torch.randn(64, 3, 32, 32, device=dev)
+    t = torch.randint(0, 10, (64,), device=dev)
+    q = harness.build_qat("resnet20", dev, qnmethod="STE", distillation=True, calib_batch=x, lr=1e-2)
+    step = harness.GraphedTrainStep(q, (x, t), seed=5)
+    try:
+        base = int(step.state[1])
+        w0 = q.model.layer1[0].conv1._modules["0"].weight.detach().clone()
+        losses = [float(step()) for _ in range(4)]
+        assert int(step.state[1]) == base + 4 * harness.GraphedTrainStep.STRIDE   # fresh noise stream per replay
+        assert all(math.isfinite(v) for v in losses)
+        assert not torch.equal(w0, q.model.layer1[0].conv1._modules["0"].weight.detach())
+        cnt = q.wrapped_criterion.cnt
+        assert torch.is_tensor(cnt) and float(cnt) >= 5      # advanced inside the graph
+        # a new batch is copied into the static buffers
+        x2 = torch.randn_like(x)
+        l2 = float(step((x2, t)))
+        assert math.isfinite(l2) and torch.equal(step.x, x2)
+    finally:
+        step.close()

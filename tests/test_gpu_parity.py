@@ -384,3 +384,44 @@ def test_rowstat_matches_torch_amin_amax_and_backward(fq, rows, inner):
     wr.grad = None
     ((wr.amin(1) * gmn).sum() + (wr * gx).sum()).backward()
     H.assert_close_rel(out2, wr.grad, 1e-6, "rowstat backward (min only)", abs_floor=1e-7)
+
+
+@pytest.mark.parametrize("rows,inner", [(1, 4096 * 3 + 4), (1, 4099), (5, 450), (3, 16384 + 512), (7, 1), (2, 8192)])
+def test_no_out_of_bounds_writes(fq, rows, inner):
+    """compute-sanitizer is closed on this pool, so bounds are checked directly: outputs are
+    carved out of sentinel-filled buffers (16-byte aligned AND deliberately misaligned) and the
+    sentinels must survive forward and backward for ragged and exact-multiple sizes."""
+    from mhaq_b200 import ops
+    n = rows * inner
+    pad = 64
+    for shift in (0, 1):                       # 1 -> data_ptr not 16-byte aligned -> scalar path
+        torch.manual_seed(n + shift)
+        def carve():
+            buf = torch.full((n + 2 * pad + shift,), 1234.5, device="cuda")
+            return buf, buf[pad + shift: pad + shift + n].view(rows, inner)
+        xb, x = carve(); x.copy_(torch.randn(rows, inner))
+        gb, go = carve(); go.copy_(torch.randn(rows, inner))
+        yb, y = carve(); cb, codes = carve(); gxb, gx = carve()
+        s = torch.full((rows, 1), 0.3, device="cuda") if rows > 1 else torch.tensor([0.3], device="cuda")
+        zp = torch.full_like(s, -1.0)
+        L = ops._Launch(x, s, zp, zp, zp + 3.0)
+        geo = L.geo
+        st = ops._stream()
+        ops.check(ops.lib.mhaq_fq_fwd_f32(x.data_ptr(), y.data_ptr(), codes.data_ptr(), *L.params(),
+                                          geo.n_rows, geo.n_inner, geo.n_ch, None, st), "fwd")
+        ws = ops._workspace(x, geo); tk = ops._tickets(x, geo)
+        out = torch.empty(4, geo.n_ch, device="cuda")
+        ops.check(ops.lib.mhaq_fq_bwd_f32(go.data_ptr(), x.data_ptr(), gx.data_ptr(), *L.params(),
+                                          geo.n_rows, geo.n_inner, geo.n_ch, 0, 0, None, 1, 2, None, None,
+                                          ws.data_ptr(), st), "bwd")
+        ops.check(ops.lib.mhaq_fq_bwd_finalize_f32(ws.data_ptr(), tk.data_ptr(), geo.n_rows, geo.n_inner,
+                                                   geo.n_ch, out[0].data_ptr(), out[1].data_ptr(),
+                                                   out[2].data_ptr(), out[3].data_ptr(), st), "fin")
+        torch.cuda.synchronize()
+        for name, buf in (("y", yb), ("codes", cb), ("gx", gxb), ("x", xb), ("go", gb)):
+            assert bool((buf[: pad + shift] == 1234.5).all()) and bool((buf[pad + shift + n:] == 1234.5).all()), \
+                f"{name}: sentinel overwritten (rows={rows}, inner={inner}, shift={shift})"
+        assert bool((tk == 0).all()), "tickets must be restored to zero"
+        # and the carved (possibly misaligned) run agrees with the oracle
+        yo = O.fake_quant(x.cpu(), s.cpu(), zp.cpu(), zp.cpu(), zp.cpu() + 3.0)
+        H.assert_bit_exact(y, yo, "y")
