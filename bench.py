@@ -495,6 +495,34 @@ def cpu_baseline(a, steps, warmup):
                       f"torch {torch.__version__} CPU, {cores} threads"}
 
 
+def cpu_config0_step():
+    """BASELINE configs[0]: ResNet-20 CIFAR-10 GDNSQ(STE) W4A4 QAT step on the CPU, synthetic
+    32x32 batch of 128, through Quantizer(config)().quantize() with every fake-quant routed
+    to the reference's eager ATen chain (oracle port) — the reference's own CPU-runnable case."""
+    from mhaq_b200 import harness
+    torch.manual_seed(0)
+    x = torch.randn(128, 3, 32, 32)
+    t = torch.randint(0, 10, (128,))
+    with _EagerReferenceBackend():
+        q = harness.build_qat("resnet20", "cpu", qnmethod="STE", act_bit=4, weight_bit=4,
+                              distillation=False, num_classes=10, calib_batch=x[:32])
+        opt = q.configure_optimizers()
+        q.train(); q.wrapped_criterion.train()
+        ts = []
+        for i in range(5):
+            t0 = time.perf_counter()
+            loss = q.training_step((x, t), 0)
+            loss.backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            ts.append(time.perf_counter() - t0)
+    ts = sorted(ts[2:])
+    med = ts[len(ts) // 2]
+    return {"workload": "configs[0] ResNet-20 CIFAR-10 GDNSQ(STE) W4A4 QAT step, batch 128, CPU",
+            "s_per_step": round(med, 3), "img_per_s": round(128 / med, 1),
+            "threads": torch.get_num_threads(), "protocol": "2 warm-up + median of 3"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -510,6 +538,11 @@ def run_reference(a):
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
+    if not a.no_resnet:
+        try:
+            out["cpu_config0_step"] = cpu_config0_step()
+        except Exception as exc:   # never let the extra leg break the contract line
+            out["cpu_config0_step"] = {"error": str(exc)[:120]}
     print(json.dumps(out), flush=True)
 
 
