@@ -452,24 +452,32 @@ __device__ __forceinline__ void flush_record(const Acc &acc, int64_t t, double *
 // to finish (ticket) sums the channel's slice records in index order and writes the
 // gradients.  Which CTA performs the last step varies run to run; the summation order, hence
 // the result, does not.  Tickets are zero on entry and restored to zero.
-constexpr int kSliceRecs = 1024;
+// one record per thread in the first stage: every load of a stage is issued at once
+// (a serial loop over records pays a full memory latency per iteration — measured 15-22 us
+// for 4096-8192 records in one CTA vs ~3 us with 256-record slices)
+constexpr int kSliceRecs = 256;
 constexpr int kFinThreads = 256;
 
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Fixed-shape tree: 5 shuffle levels inside each warp, then the warp sums (in warp-id order)
+// reduced by warp 0.  The result is valid in thread 0.  One barrier.
 template <int NCOL>
-__device__ __forceinline__ void block_sum_cols(double (&a)[NCOL], double (*s)[kFinThreads]) {
-    const int tid = threadIdx.x;
+__device__ __forceinline__ void block_sum_cols(double (&a)[NCOL], double (*s)[kFinThreads / 32]) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
-    for (int m = 0; m < NCOL; ++m) s[m][tid] = a[m];
-    __syncthreads();
-    for (int o = kFinThreads / 2; o > 0; o >>= 1) {
-        if (tid < o) {
-#pragma unroll
-            for (int m = 0; m < NCOL; ++m) s[m][tid] += s[m][tid + o];
-        }
-        __syncthreads();
+    for (int m = 0; m < NCOL; ++m) {
+        a[m] = warp_sum_f64(a[m]);
+        if (lane == 0) s[m][w] = a[m];
     }
+    __syncthreads();
+    if (w == 0) {
 #pragma unroll
-    for (int m = 0; m < NCOL; ++m) a[m] = s[m][0];
+        for (int m = 0; m < NCOL; ++m) a[m] = warp_sum_f64(lane < nw ? s[m][lane] : 0.0);
+    }
     __syncthreads();
 }
 
@@ -482,9 +490,10 @@ __device__ __forceinline__ int64_t chan_record(const Geom &g, int64_t ch, int64_
 template <int NCOL, typename Emit>
 __device__ __forceinline__ void finalize_channel(const double *ws, double *slice_ws,
                                                  unsigned int *tickets, const Geom &g, Emit emit) {
-    __shared__ double s[NCOL][kFinThreads];
+    __shared__ double s[NCOL][kFinThreads / 32];
     __shared__ int s_last;
     const int tid = threadIdx.x;
+    const int nthr = blockDim.x;
     const int64_t ch = blockIdx.y, sl = blockIdx.x, n_sl = gridDim.x;
     const int64_t recs = (g.n_rows / g.n_ch) * g.tasks_per_row;
     const int64_t i0 = sl * kSliceRecs;
@@ -492,7 +501,7 @@ __device__ __forceinline__ void finalize_channel(const double *ws, double *slice
     double a[NCOL];
 #pragma unroll
     for (int m = 0; m < NCOL; ++m) a[m] = 0.0;
-    for (int64_t i = i0 + tid; i < i1; i += kFinThreads) {
+    for (int64_t i = i0 + tid; i < i1; i += nthr) {
         const double *rec = ws + chan_record(g, ch, i) * kNPart;
 #pragma unroll
         for (int m = 0; m < NCOL; ++m) a[m] += rec[m];
@@ -514,7 +523,7 @@ __device__ __forceinline__ void finalize_channel(const double *ws, double *slice
     __threadfence();
 #pragma unroll
     for (int m = 0; m < NCOL; ++m) a[m] = 0.0;
-    for (int64_t i = tid; i < n_sl; i += kFinThreads) {
+    for (int64_t i = tid; i < n_sl; i += nthr) {
         const double *o = slice_ws + (ch * n_sl + i) * kNPart;
 #pragma unroll
         for (int m = 0; m < NCOL; ++m) a[m] += __ldcg(o + m);
@@ -1080,8 +1089,10 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets, int64_t n_rows, 
     if (n_sl > 65535 * 32 || n_ch > 65535) return MHAQ_FQ_EINVAL;
     dim3 grid((unsigned)n_sl, (unsigned)n_ch);
     double *slice_ws = ws + g.n_tasks * kNPart;
-    fq_bwd_finalize_kernel<<<grid, kFinThreads, 0, (cudaStream_t)stream>>>(ws, slice_ws, tickets, g,
-                                                                        g_scale, g_zp, g_lo, g_hi);
+    const int64_t recs = (g.n_rows / g.n_ch) * g.tasks_per_row;
+    const int threads = recs <= 64 ? 64 : (recs <= 128 ? 128 : kFinThreads);
+    fq_bwd_finalize_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(ws, slice_ws, tickets, g,
+                                                                    g_scale, g_zp, g_lo, g_hi);
     return last_error();
 }
 
