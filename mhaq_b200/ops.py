@@ -264,11 +264,8 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
     if x.numel() == 0:
         return gx, torch.zeros(4, n_ch, dtype=torch.float32, device=x.device)
     out = torch.empty(4, n_ch, dtype=torch.float32, device=x.device)   # fully written by the kernel
-    if method == METHOD_IDS["AEWGS"] and geo.axis is None:
-        raise NotImplementedError(
-            "per-tensor AEWGS reduces its statistics over dim 0 only in the reference "
-            "(gdnsq.py:150-152 with scale.shape == (1,)); not supported by the fused path yet"
-        )
+    if method == METHOD_IDS["AEWGS"] and geo.axis is None and x.dim() >= 2 and L.scale.dim() == 1:
+        return _backward_aewgs_dim0(go, x, L, code_grad, noise, need_gx, philox)
     stats = aewgs_stats(go, x, L, code_grad) if method == METHOD_IDS["AEWGS"] else None
     ws = _workspace(x, geo)
     seed = offset = 0
@@ -298,6 +295,28 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
                                        _stream()),
           "mhaq_fq_bwd_finalize_f32")
     return gx, out
+
+
+def _backward_aewgs_dim0(go, x, L: _Launch, code_grad, noise, need_gx, philox):
+    """Per-tensor AEWGS, reference quirk 9: with a scale of shape (1,) `reduce_to_shape`
+    (gdnsq.py:150-152) averages over dim 0 ONLY, i.e. the statistics (hence delta) are per
+    inner position, shared across dim 0.  Run the per-channel kernels on the transposed view
+    [P = numel/shape[0]][O = shape[0]] with channel = inner position and broadcast scalar
+    parameters, then transpose the input gradient back.  (Small weight tensors in practice.)"""
+    O_, P_ = x.shape[0], x.numel() // x.shape[0]
+    xt = x.reshape(O_, P_).t().contiguous()
+    got = go.reshape(O_, P_).t().contiguous()
+    nt = None if noise is None else noise.reshape(O_, P_).t().contiguous()
+    Lt = _Launch.__new__(_Launch)
+    Lt.geo = Geometry(P_, O_, P_, 0)
+    Lt.scale, Lt.ss, Lt.zp, Lt.zs = L.scale, 0, L.zp, 0
+    Lt.lo, Lt.ls, Lt.hi, Lt.hs = L.lo, 0, L.hi, 0
+    for p in (L.scale, L.zp, L.lo, L.hi):
+        if p is not None and p.numel() != 1:
+            raise NotImplementedError("per-tensor AEWGS expects scalar parameters")
+    gxt, out = _backward_impl(got, xt, Lt, METHOD_IDS["AEWGS"], code_grad, nt, need_gx, philox)
+    gx = None if gxt is None else gxt.t().reshape(x.shape).contiguous()
+    return gx, out.sum(dim=1, keepdim=True)
 
 
 class _FakeQuantFn(torch.autograd.Function):

@@ -240,3 +240,30 @@ def test_cuda_graph_training_step_replays_and_trains():
         assert math.isfinite(l2) and torch.equal(step.x, x2)
     finally:
         step.close()
+
+
+@pytest.mark.parametrize("scheme", ["PER_CHANNEL", "PER_TENSOR"])
+def test_noisy_linear_matches_oracle(scheme):
+    from mhaq_b200.aux.types import QScheme
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_linear import NoisyLinear
+    torch.manual_seed(4)
+    lin = NoisyLinear(40, 24, qscheme=QScheme[scheme], qnmethod=QNMethod.LSQ).cuda()
+    assert tuple(lin.log_wght_s.shape) == ((24, 1, 1, 1) if scheme == "PER_CHANNEL" else (1,))
+    with torch.no_grad():
+        lin.log_wght_s.fill_(-3.0)
+    lin.train()
+    x = torch.randn(6, 40, device="cuda")
+    go = torch.randn(6, 24, device="cuda")
+    out = lin(x)
+    out.backward(go)
+    w = lin.weight.detach().cpu().clone().requires_grad_(True)
+    ls = lin.log_wght_s.detach().cpu().clone().requires_grad_(True)
+    s = torch.exp2(ls).reshape(24, 1) if scheme == "PER_CHANNEL" else torch.exp2(ls)
+    zp = w.amin(1, keepdim=True) if scheme == "PER_CHANNEL" else w.amin()
+    wq = O.fake_quant(w, s, zp, -math.inf, math.inf, "LSQ")
+    ref = torch.nn.functional.linear(x.cpu(), wq, lin.bias.detach().cpu())
+    ref.backward(go.cpu())
+    assert_bit_exact(lin.quantized_weight(), wq, "wq")
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=1e-4)    # GEMM: TF32 vs fp32
+    assert_close_rel(lin.weight.grad, w.grad, 1e-3, "g_weight", abs_floor=2e-3)

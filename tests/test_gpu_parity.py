@@ -425,3 +425,26 @@ def test_no_out_of_bounds_writes(fq, rows, inner):
         # and the carved (possibly misaligned) run agrees with the oracle
         yo = O.fake_quant(x.cpu(), s.cpu(), zp.cpu(), zp.cpu(), zp.cpu() + 3.0)
         H.assert_bit_exact(y, yo, "y")
+
+
+def test_per_tensor_aewgs_dim0_statistics_quirk(fq):
+    """Reference quirk 9: scale of shape (1,) -> AEWGS statistics are averaged over dim 0 only
+    (gdnsq.py:150-152), i.e. delta is per inner position."""
+    torch.manual_seed(21)
+    w = torch.randn(12, 5, 3, 3) * 0.4
+    go = torch.randn_like(w)
+    r = torch.randint(0, 2, w.shape).float() - 0.5
+    log_s = torch.tensor([-2.0])
+
+    def run(fn, dev):
+        wr = w.to(dev).clone().requires_grad_(True)
+        ls = log_s.to(dev).clone().requires_grad_(True)
+        s = torch.exp2(ls)
+        y = fn(wr, s, wr.amin(), -math.inf, math.inf, method="AEWGS", noise=r.to(dev))
+        y.backward(go.to(dev))
+        return y.detach(), wr.grad, ls.grad
+    y_o, gw_o, gs_o = run(O.fake_quant, "cpu")
+    y_g, gw_g, gs_g = run(fq.fake_quant, "cuda")
+    H.assert_bit_exact(y_g, y_o, "y")
+    H.assert_close_rel(gw_g, gw_o, REL, "g_weight", abs_floor=2e-6)
+    H.assert_close_rel(gs_g, gs_o, REL, "g_log_s", abs_floor=2e-5)
