@@ -448,3 +448,27 @@ def test_per_tensor_aewgs_dim0_statistics_quirk(fq):
     H.assert_bit_exact(y_g, y_o, "y")
     H.assert_close_rel(gw_g, gw_o, REL, "g_weight", abs_floor=2e-6)
     H.assert_close_rel(gs_g, gs_o, REL, "g_log_s", abs_floor=2e-5)
+
+
+@pytest.mark.parametrize("shape,per_channel,clip", [((24, 20000), True, False), ((1, 1 << 20), False, True),
+                                                     ((16, 8, 3, 3), True, False)])
+def test_host_streaming_api_matches_device_api(fq, shape, per_channel, clip):
+    """The pipelined host-buffer entry (bench `e2e`) must give the device API's results."""
+    from mhaq_b200.host import fake_quant_fwd_bwd_host
+    x, go, _, scale, zp, lo, hi, _ = _leafs(shape, per_channel, 4, clip, 17, "cpu")
+    dev = "cuda"
+    P = [None if p is None else p.to(dev) for p in (scale, zp, lo, hi)]
+    # device API (fused Philox with the same per-chunk streams is not comparable: use LSQ)
+    xs = x.to(dev).requires_grad_(True)
+    Pd = [None if p is None else p.clone().requires_grad_(True) for p in P]
+    y = fq.fake_quant(xs, Pd[0], Pd[1], -math.inf if Pd[2] is None else Pd[2],
+                      math.inf if Pd[3] is None else Pd[3], method="LSQ")
+    y.backward(go.to(dev))
+    hy, hgx, grads = fake_quant_fwd_bwd_host(x.pin_memory(), go.pin_memory(), P[0], P[1], P[2], P[3],
+                                             method="LSQ", chunks=5)
+    torch.cuda.synchronize()
+    H.assert_bit_exact(hy, y, "y")
+    H.assert_bit_exact(hgx, xs.grad, "gx")
+    for k, p in zip(("scale", "zero_point", "min_val", "max_val"), Pd):
+        if p is not None:
+            H.assert_close_rel(grads[k], p.grad, 1e-5, k, abs_floor=1e-5)
