@@ -55,6 +55,9 @@ def parse_args():
                          "(CIFAR-100-shaped; use --qat-method AEWGS --qat-bits 1)")
     ap.add_argument("--qat-method", default="STE", choices=["STE", "LSQ", "AEWGS", "EWGS"])
     ap.add_argument("--qat-bits", type=int, default=4)
+    ap.add_argument("--ddp-reference-flags", action="store_true",
+                    help="wrap DDP exactly like the reference's Trainer (find_unused_parameters=True, "
+                         "buffer broadcast every step) instead of the lean wrapping")
     ap.add_argument("--graph", action="store_true",
                     help="QAT leg: capture the whole training step in a CUDA graph (single GPU)")
     ap.add_argument("--no-eager-ref", action="store_true",
@@ -222,9 +225,7 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
                           weight_bit=a.qat_bits, distillation=True, num_classes=classes,
                           calib_batch=x[: min(B, 64)])
     if use_dist:
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        q.model = DDP(q.model, device_ids=[dev.index], find_unused_parameters=True,
-                      gradient_as_bucket_view=True)
+        q.model = harness.wrap_ddp(q.model, dev, lean=not a.ddp_reference_flags)
     graphed = None
     if a.graph and not use_dist:
         graphed = harness.GraphedTrainStep(q, (x, t), seed=1234)

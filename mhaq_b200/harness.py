@@ -184,18 +184,34 @@ def build_qat(model_name="resnet18", device="cuda", qnmethod="STE", act_bit=4, w
     return qmodel
 
 
+def wrap_ddp(model: nn.Module, device, lean: bool = True):
+    """DistributedDataParallel around the quantized model.
+
+    The reference's Trainer passes ``find_unused_parameters=True`` (training/trainer.py:93-95)
+    only because every per-channel ``NoisyConv2d`` owns a trainable ``log_b_s`` that is never
+    used; that flag makes DDP walk the autograd graph on every step.
+    ``lean=True`` instead tells DDP to ignore exactly those parameters, and skips the per-step
+    broadcast of BatchNorm running statistics (they do not enter the training arithmetic).
+    ``lean=False`` reproduces the reference's flags."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    ids = [device.index] if device is not None and device.type == "cuda" else None
+    if not lean:
+        return DDP(model, device_ids=ids, find_unused_parameters=True, gradient_as_bucket_view=True)
+    ignore = [n for n, _ in model.named_parameters() if n.endswith("log_b_s")]
+    DDP._set_params_and_buffers_to_ignore_for_model(model, ignore)
+    return DDP(model, device_ids=ids, find_unused_parameters=False, broadcast_buffers=False,
+               gradient_as_bucket_view=True)
+
+
 def fit_steps(qmodel: LModule, batches, ddp: bool = False, device=None, on_step=None,
               sync_bn: bool = False):
     """Run the training steps in Lightning's order.  `batches`: iterable of (inputs, target).
     Under DDP the quantized model is wrapped like Lightning's DDPStrategy does
     (find_unused_parameters=True: the reference's never-used `log_b_s`, trainer.py:93-95)."""
     if ddp:
-        from torch.nn.parallel import DistributedDataParallel as DDP
         if sync_bn:
             qmodel.model = nn.SyncBatchNorm.convert_sync_batchnorm(qmodel.model)
-        inner = qmodel.model
-        qmodel.model = DDP(inner, device_ids=[device.index] if device is not None else None,
-                           find_unused_parameters=True, gradient_as_bucket_view=True)
+        qmodel.model = wrap_ddp(qmodel.model, device, lean=False)
     opt = qmodel.configure_optimizers()
     qmodel.train()
     if hasattr(qmodel, "wrapped_criterion"):
