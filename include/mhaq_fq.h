@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define MHAQ_FQ_ABI_VERSION 2
+#define MHAQ_FQ_ABI_VERSION 3
 
 /* gradient estimators — numeric values follow the reference enum
  * QNMethod (src/quantization/gdnsq/gdnsq_utils.py:9-13). */
@@ -55,6 +55,22 @@ extern "C" {
 #define MHAQ_FQ_EWGS 1
 #define MHAQ_FQ_AEWGS 2
 #define MHAQ_FQ_LSQ 3
+
+/* How the parameter pointers are interpreted (`param_mode`).
+ *   LINEAR     scale, zp, lo, hi as described under Conventions.
+ *   ACT_LOG    the NoisyAct parameters (layers/gdnsq_act.py:42-48), one float each:
+ *              scale -> log_act_s, zp -> act_b, lo -> log_act_q, hi unused (n_ch must be 1);
+ *              the kernels form s = exp2(log_act_s), q = exp2(log_act_q), zero_point =
+ *              min_val = act_b, max_val = (act_b + q) - s themselves, and the finalize returns
+ *              g_scale = d/d log_act_s, g_zp = d/d act_b, g_lo = d/d log_act_q (g_hi unused).
+ *   WEIGHT_LOG scale -> log_wght_s[ch] (layers/gdnsq_conv2d.py:72), zp -> zero point per
+ *              channel, lo = hi = NULL; the finalize returns g_scale = d/d log_wght_s,
+ *              g_zp = d/d zero_point.
+ * The log modes remove the ~25 tiny elementwise launches autograd otherwise runs per quantizer
+ * for exp2 / add / sub and their backward. */
+#define MHAQ_FQ_PARAMS_LINEAR 0
+#define MHAQ_FQ_PARAMS_ACT_LOG 1
+#define MHAQ_FQ_PARAMS_WEIGHT_LOG 2
 
 /* argument errors */
 #define MHAQ_FQ_EINVAL (-1)
@@ -86,7 +102,7 @@ int64_t mhaq_fq_ticket_count(int64_t n_rows, int64_t n_inner, int64_t n_ch);
  *            mhaq_fq_minmax_finalize (eval mode). */
 int mhaq_fq_fwd_f32(const float *x, float *y, float *codes,
                     const float *scale, const float *zp, const float *lo, const float *hi,
-                    int scale_stride, int zp_stride, int lo_stride, int hi_stride,
+                    int scale_stride, int zp_stride, int lo_stride, int hi_stride, int param_mode,
                     int64_t n_rows, int64_t n_inner, int64_t n_ch,
                     double *minmax_ws, void *stream);
 
@@ -110,7 +126,7 @@ int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_i
  *   ws      : workspace, consumed by mhaq_fq_bwd_finalize_f32. */
 int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx,
                     const float *scale, const float *zp, const float *lo, const float *hi,
-                    int scale_stride, int zp_stride, int lo_stride, int hi_stride,
+                    int scale_stride, int zp_stride, int lo_stride, int hi_stride, int param_mode,
                     int64_t n_rows, int64_t n_inner, int64_t n_ch,
                     int method, int go_is_code_grad,
                     const float *r, uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
@@ -122,6 +138,9 @@ int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx,
  * Each output is [n_ch] floats (or NULL to skip):
  *   g_scale = d/d scale,  g_zp = d/d zero_point,  g_lo = d/d min_val,  g_hi = d/d max_val. */
 int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets,
+                             const float *scale, const float *zp, const float *lo, const float *hi,
+                             int scale_stride, int zp_stride, int lo_stride, int hi_stride,
+                             int param_mode,     /* parameters only read in the log modes */
                              int64_t n_rows, int64_t n_inner, int64_t n_ch,
                              float *g_scale, float *g_zp, float *g_lo, float *g_hi,
                              void *stream);
@@ -130,7 +149,7 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets,
 int mhaq_fq_aewgs_stats_f32(const float *go, const float *x,
                             const float *scale, const float *zp, const float *lo, const float *hi,
                             int scale_stride, int zp_stride, int lo_stride, int hi_stride,
-                            int64_t n_rows, int64_t n_inner, int64_t n_ch,
+                            int param_mode, int64_t n_rows, int64_t n_inner, int64_t n_ch,
                             int go_is_code_grad, double *ws, void *stream);
 
 /* stats[0*n_ch+c]=mean num, stats[1*n_ch+c]=mean e2, stats[2*n_ch+c]=mean e. */

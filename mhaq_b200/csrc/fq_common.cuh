@@ -76,9 +76,21 @@ __host__ __device__ inline Geom make_geom(int64_t n_rows, int64_t n_inner, int64
     return g;
 }
 
+// How the four parameter pointers are interpreted (MHAQ_FQ_PARAMS_* in the header).
+//   LINEAR : scale, zero_point, min_val, max_val as given (strides 0/1)
+//   ACT_LOG: the three NoisyAct parameters (gdnsq_act.py:42-48), each one float:
+//              scale -> log_act_s,  zp -> act_b,  lo -> log_act_q,  hi unused
+//            s = exp2(log_act_s), q = exp2(log_act_q), zp = lo = act_b, hi = (act_b + q) - s
+//   WEIGHT_LOG: scale -> log_wght_s[ch] (stride 0/1), zp -> zero point (row minimum), no clamp
+//            s = exp2(log_wght_s)                               (gdnsq_conv2d.py:72, 80-84)
+// exp2f is the same libdevice routine torch's CUDA exp2 kernel calls, so the scale has the
+// same bits as torch.exp2(log_s) (checked by tests/test_gpu_layers.py).
+enum { PARAMS_LINEAR = 0, PARAMS_ACT_LOG = 1, PARAMS_WEIGHT_LOG = 2 };
+
 struct QParams {
     const float *scale, *zp, *lo, *hi;
     int ss, zs, ls, hs;
+    int mode;
 };
 
 // Per-channel constants held in registers for the lifetime of a task.
@@ -88,7 +100,16 @@ struct QConst {
 
 __device__ __forceinline__ QConst load_qconst(const QParams &p, int64_t ch) {
     QConst q;
-    q.s = __ldg(p.scale + ch * p.ss);
+    if (p.mode == PARAMS_ACT_LOG) {
+        const float b = __ldg(p.zp);
+        q.s = exp2f(__ldg(p.scale));
+        q.zp = b;
+        q.lo = b;
+        q.hi = __fsub_rn(__fadd_rn(b, exp2f(__ldg(p.lo))), q.s);      // (act_b + q) - s
+        return q;
+    }
+    const float sv = __ldg(p.scale + ch * p.ss);
+    q.s = (p.mode == PARAMS_WEIGHT_LOG) ? exp2f(sv) : sv;
     q.zp = __ldg(p.zp + ch * p.zs);
     q.lo = p.lo ? __ldg(p.lo + ch * p.ls) : -INFINITY;
     q.hi = p.hi ? __ldg(p.hi + ch * p.hs) : INFINITY;

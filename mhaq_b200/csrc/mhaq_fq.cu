@@ -535,15 +535,36 @@ __device__ __forceinline__ void finalize_channel(const double *ws, double *slice
     }
 }
 
+// Outputs by parameter mode (a[] = {S_e, S_noise, S_zp, S_lo, S_hi} of the channel):
+//   LINEAR    : o0 = d/d scale, o1 = d/d zero_point, o2 = d/d min_val, o3 = d/d max_val
+//   ACT_LOG   : o0 = d/d log_act_s = (d/ds - S_hi) * s * ln2      (hi contains -s)
+//               o1 = d/d act_b     = S_zp + S_lo + S_hi           (zp, lo and hi all contain act_b)
+//               o2 = d/d log_act_q = S_hi * q * ln2
+//   WEIGHT_LOG: o0 = d/d log_wght_s = d/ds * s * ln2,  o1 = d/d zero_point
+// i.e. the Exp2Backward / AddBackward / SubBackward nodes autograd would run on the tiny
+// parameter tensors (gdnsq_act.py:42-48), folded into the last thread of the reduction.
 __global__ void __launch_bounds__(kFinThreads)
 fq_bwd_finalize_kernel(const double *__restrict__ ws, double *slice_ws, unsigned int *tickets,
-                       Geom g, float *__restrict__ g_scale, float *__restrict__ g_zp,
-                       float *__restrict__ g_lo, float *__restrict__ g_hi) {
+                       Geom g, QParams prm, float *__restrict__ o0, float *__restrict__ o1,
+                       float *__restrict__ o2, float *__restrict__ o3) {
     finalize_channel<5>(ws, slice_ws, tickets, g, [=](int64_t ch, const double (&a)[5]) {
-        if (g_scale) g_scale[ch] = (float)(a[0] + a[1]);
-        if (g_zp) g_zp[ch] = (float)a[2];
-        if (g_lo) g_lo[ch] = (float)a[3];
-        if (g_hi) g_hi[ch] = (float)a[4];
+        const double ds = a[0] + a[1];
+        constexpr double kLn2 = 0.693147180559945309417;
+        if (prm.mode == PARAMS_ACT_LOG) {
+            const double s = (double)exp2f(prm.scale[0]), q = (double)exp2f(prm.lo[0]);
+            if (o0) o0[0] = (float)((ds - a[4]) * s * kLn2);
+            if (o1) o1[0] = (float)(a[2] + a[3] + a[4]);
+            if (o2) o2[0] = (float)(a[4] * q * kLn2);
+        } else if (prm.mode == PARAMS_WEIGHT_LOG) {
+            const double s = (double)exp2f(prm.scale[ch * prm.ss]);
+            if (o0) o0[ch] = (float)(ds * s * kLn2);
+            if (o1) o1[ch] = (float)a[2];
+        } else {
+            if (o0) o0[ch] = (float)ds;
+            if (o1) o1[ch] = (float)a[2];
+            if (o2) o2[ch] = (float)a[3];
+            if (o3) o3[ch] = (float)a[4];
+        }
     });
 }
 
@@ -911,6 +932,17 @@ inline int check_common(const void *x, const float *scale, const float *zp, int6
     return 0;
 }
 inline bool stride_ok(int s) { return s == 0 || s == 1; }
+inline bool mode_ok(int m) { return m >= PARAMS_LINEAR && m <= PARAMS_WEIGHT_LOG; }
+// ACT_LOG needs all of log_act_s (scale), act_b (zp) and log_act_q (lo) and is per-tensor
+inline int check_mode(int mode, const float *lo, int64_t n_ch) {
+    if (!mode_ok(mode)) return MHAQ_FQ_EINVAL;
+    if (mode == PARAMS_ACT_LOG && !lo) return MHAQ_FQ_ENULL;
+    if (mode == PARAMS_ACT_LOG && n_ch != 1) return MHAQ_FQ_EINVAL;
+    return 0;
+}
+inline bool has_clamp(int mode, const float *lo, const float *hi) {
+    return mode == PARAMS_ACT_LOG || (mode == PARAMS_LINEAR && (lo != nullptr || hi != nullptr));
+}
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 inline int grid_for(int64_t n_tasks) {
@@ -1009,21 +1041,22 @@ int64_t mhaq_fq_ticket_count(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
 
 int mhaq_fq_fwd_f32(const float *x, float *y, float *codes, const float *scale, const float *zp,
                     const float *lo, const float *hi, int scale_stride, int zp_stride,
-                    int lo_stride, int hi_stride, int64_t n_rows, int64_t n_inner, int64_t n_ch,
-                    double *minmax_ws, void *stream) {
+                    int lo_stride, int hi_stride, int param_mode, int64_t n_rows, int64_t n_inner,
+                    int64_t n_ch, double *minmax_ws, void *stream) {
     int rc = check_common(x, scale, zp, n_rows, n_inner, n_ch);
     if (rc) return rc;
+    if ((rc = check_mode(param_mode, lo, n_ch)) != 0) return rc;
     if (!stride_ok(scale_stride) || !stride_ok(zp_stride) || !stride_ok(lo_stride) ||
         !stride_ok(hi_stride))
         return MHAQ_FQ_EINVAL;
     if (n_rows == 0 || n_inner == 0) return 0;
     const Geom g = stream_geom(n_rows, n_inner, n_ch);
-    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride};
+    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode};
     const bool vec = (n_inner % 4 == 0) && aligned16(x) && (!y || aligned16(y)) &&
                      (!codes || aligned16(codes));
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(g.n_tasks);
-    const bool clamp = (lo != nullptr) || (hi != nullptr);
+    const bool clamp = has_clamp(param_mode, lo, hi);
     if (vec && clamp)
         fq_fwd_kernel<true, true><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
     else if (vec)
@@ -1044,12 +1077,13 @@ int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_i
 
 int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx, const float *scale,
                     const float *zp, const float *lo, const float *hi, int scale_stride,
-                    int zp_stride, int lo_stride, int hi_stride, int64_t n_rows, int64_t n_inner,
-                    int64_t n_ch, int method, int go_is_code_grad, const float *r, uint64_t seed,
-                    uint64_t offset, const uint64_t *philox_dev, const float *aewgs_stats,
-                    double *ws, void *stream) {
+                    int zp_stride, int lo_stride, int hi_stride, int param_mode, int64_t n_rows,
+                    int64_t n_inner, int64_t n_ch, int method, int go_is_code_grad, const float *r,
+                    uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                    const float *aewgs_stats, double *ws, void *stream) {
     int rc = check_common(x, scale, zp, n_rows, n_inner, n_ch);
     if (rc) return rc;
+    if ((rc = check_mode(param_mode, lo, n_ch)) != 0) return rc;
     if (!go || !ws) return MHAQ_FQ_ENULL;
     if (!stride_ok(scale_stride) || !stride_ok(zp_stride) || !stride_ok(lo_stride) ||
         !stride_ok(hi_stride))
@@ -1058,10 +1092,10 @@ int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx, const float *sca
     if (method == MHAQ_FQ_AEWGS && !aewgs_stats) return MHAQ_FQ_ENULL;
     if (n_rows == 0 || n_inner == 0) return 0;
     const Geom g = reduce_geom(n_rows, n_inner, n_ch);
-    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride};
+    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode};
     const bool vec = (n_inner % 4 == 0) && aligned16(x) && aligned16(go) &&
                      (!gx || aligned16(gx)) && (!r || aligned16(r));
-    const bool clamp = (lo != nullptr) || (hi != nullptr);
+    const bool clamp = has_clamp(param_mode, lo, hi);
     const bool er = (r != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(g.n_tasks);
@@ -1079,11 +1113,17 @@ int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx, const float *sca
 #undef MHAQ_BWD
 }
 
-int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets, int64_t n_rows, int64_t n_inner,
-                             int64_t n_ch, float *g_scale, float *g_zp, float *g_lo, float *g_hi,
-                             void *stream) {
+int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets, const float *scale, const float *zp,
+                             const float *lo, const float *hi, int scale_stride, int zp_stride,
+                             int lo_stride, int hi_stride, int param_mode, int64_t n_rows,
+                             int64_t n_inner, int64_t n_ch, float *g_scale, float *g_zp, float *g_lo,
+                             float *g_hi, void *stream) {
     if (!ws || !tickets) return MHAQ_FQ_ENULL;
     if (n_rows <= 0 || n_inner <= 0 || n_ch < 1 || (n_rows % n_ch) != 0) return MHAQ_FQ_EINVAL;
+    int rc = check_mode(param_mode, lo, n_ch);
+    if (rc) return rc;
+    if (param_mode != PARAMS_LINEAR && !scale) return MHAQ_FQ_ENULL;
+    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode};
     const Geom g = reduce_geom(n_rows, n_inner, n_ch);
     const int64_t n_sl = n_slices_of(g);
     if (n_sl > 65535 * 32 || n_ch > 65535) return MHAQ_FQ_EINVAL;
@@ -1091,21 +1131,23 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets, int64_t n_rows, 
     double *slice_ws = ws + g.n_tasks * kNPart;
     const int64_t recs = (g.n_rows / g.n_ch) * g.tasks_per_row;
     const int threads = recs <= 64 ? 64 : (recs <= 128 ? 128 : kFinThreads);
-    fq_bwd_finalize_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(ws, slice_ws, tickets, g,
+    fq_bwd_finalize_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(ws, slice_ws, tickets, g, prm,
                                                                     g_scale, g_zp, g_lo, g_hi);
     return last_error();
 }
 
 int mhaq_fq_aewgs_stats_f32(const float *go, const float *x, const float *scale, const float *zp,
                             const float *lo, const float *hi, int scale_stride, int zp_stride,
-                            int lo_stride, int hi_stride, int64_t n_rows, int64_t n_inner,
-                            int64_t n_ch, int go_is_code_grad, double *ws, void *stream) {
+                            int lo_stride, int hi_stride, int param_mode, int64_t n_rows,
+                            int64_t n_inner, int64_t n_ch, int go_is_code_grad, double *ws,
+                            void *stream) {
     int rc = check_common(x, scale, zp, n_rows, n_inner, n_ch);
     if (rc) return rc;
+    if ((rc = check_mode(param_mode, lo, n_ch)) != 0) return rc;
     if (!go || !ws) return MHAQ_FQ_ENULL;
     if (n_rows == 0 || n_inner == 0) return 0;
     const Geom g = stream_geom(n_rows, n_inner, n_ch);
-    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride};
+    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode};
     const bool vec = (n_inner % 4 == 0) && aligned16(x) && aligned16(go);
     const int grid = grid_for(g.n_tasks);
     cudaStream_t st = (cudaStream_t)stream;

@@ -110,9 +110,10 @@ def fake_quant_fwd_bwd_host(x_host: torch.Tensor, go_host: torch.Tensor, scale, 
                                           geo.n_rows, geo.n_inner, geo.n_ch, mid, 0, None,
                                           philox[0], philox[1] + i, None, None, ws.data_ptr(),
                                           ops._stream()), "mhaq_fq_bwd_f32")
-        ops.check(ops.lib.mhaq_fq_bwd_finalize_f32(ws.data_ptr(), tk.data_ptr(), geo.n_rows, geo.n_inner,
-                                                   geo.n_ch, out[0].data_ptr(), out[1].data_ptr(),
-                                                   out[2].data_ptr(), out[3].data_ptr(), ops._stream()),
+        ops.check(ops.lib.mhaq_fq_bwd_finalize_f32(ws.data_ptr(), tk.data_ptr(), *L.params(), geo.n_rows,
+                                                   geo.n_inner, geo.n_ch, out[0].data_ptr(),
+                                                   out[1].data_ptr(), out[2].data_ptr(),
+                                                   out[3].data_ptr(), ops._stream()),
                   "mhaq_fq_bwd_finalize_f32")
         ev_done[i].record(cur)
         for j, k in enumerate(("scale", "zero_point", "min_val", "max_val")):

@@ -184,8 +184,13 @@ def reset_philox_call_counter() -> None:
         _philox_call[k] = 0
 
 
+PARAMS_LINEAR, PARAMS_ACT_LOG, PARAMS_WEIGHT_LOG = 0, 1, 2
+
+
 class _Launch:
     """Flattened, validated launch description shared by forward and backward."""
+
+    mode = PARAMS_LINEAR
 
     def __init__(self, x, scale, zp, lo, hi):
         _require_cuda(x)
@@ -197,9 +202,40 @@ class _Launch:
         if self.scale is None or self.zp is None:
             raise RuntimeError("scale and zero_point are required")
 
+    @classmethod
+    def act_log(cls, x, log_act_s, log_act_q, act_b):
+        """MHAQ_FQ_PARAMS_ACT_LOG: the kernels read the three NoisyAct parameters directly."""
+        _require_cuda(x)
+        L = cls.__new__(cls)
+        L.mode = PARAMS_ACT_LOG
+        L.geo = Geometry(1, x.numel(), 1, None)
+        L.scale, L.ss = _prep_param(log_act_s, x, "scale")
+        L.zp, L.zs = _prep_param(act_b, x, "zp")
+        L.lo, L.ls = _prep_param(log_act_q, x, "lo_param")
+        L.hi, L.hs = None, 0
+        if not (L.scale.numel() == L.zp.numel() == L.lo.numel() == 1):
+            raise RuntimeError("NoisyAct parameters must have one element each")
+        return L
+
+    @classmethod
+    def weight_log(cls, w, log_wght_s, zp_rows):
+        """MHAQ_FQ_PARAMS_WEIGHT_LOG: per-channel (dim 0) log-scale, zero point per row."""
+        _require_cuda(w)
+        L = cls.__new__(cls)
+        L.mode = PARAMS_WEIGHT_LOG
+        rows = w.shape[0]
+        L.geo = Geometry(rows, w.numel() // rows if rows else 0, rows, 0)
+        L.scale, L.ss = _prep_param(log_wght_s, w, "scale")
+        L.zp, L.zs = _prep_param(zp_rows, w, "zp")
+        L.lo = L.hi = None
+        L.ls = L.hs = 0
+        if L.scale.numel() != rows or L.zp.numel() != rows:
+            raise RuntimeError("per-channel weight parameters must have one entry per row of dim 0")
+        return L
+
     def params(self):
         return (_ptr(self.scale), _ptr(self.zp), _ptr(self.lo), _ptr(self.hi),
-                self.ss, self.zs, self.ls, self.hs)
+                self.ss, self.zs, self.ls, self.hs, self.mode)
 
 
 def _forward_impl(x, L: _Launch, want_y: bool, want_codes: bool, want_minmax: bool):
@@ -290,9 +326,9 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
                               geo.n_rows, geo.n_inner, geo.n_ch, method, int(code_grad),
                               _ptr(noise), seed, offset, _ptr(pdev), _ptr(stats), _ptr(ws), _stream()),
           "mhaq_fq_bwd_f32")
-    check(lib.mhaq_fq_bwd_finalize_f32(_ptr(ws), _ptr(tk), geo.n_rows, geo.n_inner, geo.n_ch,
-                                       _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]),
-                                       _stream()),
+    check(lib.mhaq_fq_bwd_finalize_f32(_ptr(ws), _ptr(tk), *L.params(), geo.n_rows, geo.n_inner,
+                                       geo.n_ch, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
+                                       _ptr(out[3]), _stream()),
           "mhaq_fq_bwd_finalize_f32")
     return gx, out
 
@@ -483,3 +519,84 @@ def weight_fake_quant(w, scale, method="STE", noise=None, philox=None):
     if scale.numel() != w.shape[0]:
         raise RuntimeError("weight_fake_quant expects one scale per output channel (dim 0)")
     return _WeightFakeQuantFn.apply(w, scale, _method_id(method), noise, philox)
+
+
+class _ActFakeQuantFn(torch.autograd.Function):
+    """NoisyAct.forward's arithmetic (gdnsq_act.py:42-55) as ONE autograd node: the kernels read
+    log_act_s / log_act_q / act_b directly (MHAQ_FQ_PARAMS_ACT_LOG) and the finalize returns
+    the log-domain gradients, so none of the ~25 tiny exp2/add/sub launches (forward and
+    backward) autograd would otherwise run per quantizer exist."""
+
+    @staticmethod
+    def forward(ctx, x, log_act_s, log_act_q, act_b, method, noise, philox):
+        x = x.contiguous()
+        L = _Launch.act_log(x, log_act_s, log_act_q, act_b)
+        y, _, _ = _forward_impl(x, L, True, False, False)
+        ctx.save_for_backward(x, log_act_s, log_act_q, act_b)
+        ctx.L, ctx.method, ctx.noise, ctx.philox = L, method, noise, philox
+        return y
+
+    @staticmethod
+    def backward(ctx, go):
+        x, log_act_s, log_act_q, act_b = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        gx, out = _backward_impl(go, x, ctx.L, ctx.method, False, ctx.noise, need[0], ctx.philox)
+        return (gx if need[0] else None,
+                out[0].reshape(log_act_s.shape) if need[1] else None,
+                out[2].reshape(log_act_q.shape) if need[2] else None,
+                out[1].reshape(act_b.shape) if need[3] else None, None, None, None)
+
+
+def act_fake_quant(x, log_act_s, log_act_q, act_b, method="STE", noise=None, philox=None):
+    """Fused NoisyAct: fake_quant(x, s=2^log_act_s, zp=lo=act_b, hi=act_b+2^log_act_q-s)."""
+    _require_cuda(x)
+    return _ActFakeQuantFn.apply(x, log_act_s, log_act_q, act_b, _method_id(method), noise, philox)
+
+
+class _WeightLogFakeQuantFn(torch.autograd.Function):
+    """_WeightFakeQuantFn with the scale in the log domain (MHAQ_FQ_PARAMS_WEIGHT_LOG):
+    (wq, row_min, row_max) from (weight, log_wght_s), d/d log_wght_s straight from the kernel."""
+
+    @staticmethod
+    def forward(ctx, w, log_wght_s, method, noise, philox):
+        ctx.set_materialize_grads(False)
+        w = w.contiguous()
+        rows = w.shape[0]
+        mn, mx, cmn, cmx = row_stats(w.view(rows, -1))
+        L = _Launch.weight_log(w, log_wght_s, mn)
+        wq, _, _ = _forward_impl(w, L, True, False, False)
+        ctx.save_for_backward(w, log_wght_s, mn, mx, cmn, cmx)
+        ctx.L, ctx.method, ctx.noise, ctx.philox = L, method, noise, philox
+        return wq, mn, mx
+
+    @staticmethod
+    def backward(ctx, g_wq, g_mn, g_mx):
+        w, log_wght_s, mn, mx, cmn, cmx = ctx.saved_tensors
+        rows = w.shape[0]
+        w2 = w.view(rows, -1)
+        g_log_s = None
+        if g_wq is not None:
+            gx, out = _backward_impl(g_wq, w, ctx.L, ctx.method, False, ctx.noise, True, ctx.philox)
+            g_log_s = out[0].reshape(log_wght_s.shape)
+            g_min = out[1] if g_mn is None else out[1] + g_mn
+            gx2 = gx.view(rows, -1)
+        else:
+            gx2, g_min = None, g_mn
+        if not ctx.needs_input_grad[0]:
+            return None, g_log_s, None, None, None
+        if g_min is None and g_mx is None:
+            gw = torch.zeros_like(w) if gx2 is None else gx2.view_as(w)
+        else:
+            gw = row_stats_backward(gx2, w2, mn if g_min is not None else None,
+                                    cmn if g_min is not None else None, g_min,
+                                    mx if g_mx is not None else None,
+                                    cmx if g_mx is not None else None, g_mx).view_as(w)
+        return gw, (g_log_s if ctx.needs_input_grad[1] else None), None, None, None
+
+
+def weight_fake_quant_log(w, log_wght_s, method="STE", noise=None, philox=None):
+    """(wq, row_min, row_max) for a per-channel weight from its LOG scale (channel = dim 0)."""
+    _require_cuda(w)
+    if log_wght_s.numel() != w.shape[0]:
+        raise RuntimeError("weight_fake_quant_log expects one log-scale per output channel (dim 0)")
+    return _WeightLogFakeQuantFn.apply(w, log_wght_s, _method_id(method), noise, philox)

@@ -65,6 +65,7 @@ def scaled_noise(x, s):
 class Quantizer:
     def __init__(self, module, scale, zero_point, min_val, max_val,
                  rnoise_ratio=torch.Tensor([-1.0]), qnmethod: QNMethod = QNMethod.STE) -> None:
+        self._lazy = None
         self.module = module
         self.scale = scale
         self.zero_point = zero_point
@@ -74,6 +75,37 @@ class Quantizer:
         # evaluated once at construction, exactly like the reference (gdnsq.py:186)
         self.positive_scale = torch.all(torch.as_tensor(self.scale) > 0).item()
         self.qnmethod = qnmethod
+
+    # The four operands stay ordinary read/write attributes (the reference's layers assign
+    # them before every call, gdnsq_act.py:45-48).  The fused layer paths hand the kernels the
+    # log-domain parameters instead and only *defer* these assignments: `defer(fn)` installs a
+    # thunk that produces (scale, zero_point, min_val, max_val) — with autograd history, exactly
+    # what the reference would have assigned — the first time any of them is read.
+    def defer(self, fn) -> None:
+        self._lazy = fn
+
+    def _resolve(self):
+        fn = self._lazy
+        if fn is not None:
+            self._lazy = None
+            self._scale, self._zero_point, self._min_val, self._max_val = fn()
+
+    def _get(name):
+        def getter(self):
+            self._resolve()
+            return getattr(self, "_" + name)
+
+        def setter(self, value):
+            self._resolve()
+            setattr(self, "_" + name, value)
+
+        return property(getter, setter)
+
+    scale = _get("scale")
+    zero_point = _get("zero_point")
+    min_val = _get("min_val")
+    max_val = _get("max_val")
+    del _get
 
     # -- helpers ---------------------------------------------------------------------------
     def _method(self):
@@ -136,12 +168,20 @@ class Quantizer:
         return ops.fake_quant(value, self.scale, self._zp_like(value), self.min_val, self.max_val,
                               method=self._method(), noise=noise)
 
-    def fake_quant_weight(self, weight, noise=None):
-        """Per-channel weight path with the row-minimum zero point computed in the same
-        pass (reads self.scale; sets self.zero_point like NoisyConv2d.forward does,
-        gdnsq_conv2d.py:80-84).  Returns (weight_q, row_min, row_max)."""
-        wq, mn, mx = ops.weight_fake_quant(weight, self.scale, method=self._method(), noise=noise)
-        self.zero_point = mn.view((weight.shape[0],) + (1,) * (weight.dim() - 1))
+    def fake_quant_weight(self, weight, log_scale=None, noise=None):
+        """Per-channel weight path with the row-minimum zero point computed in the same pass
+        (sets self.zero_point like NoisyConv2d.forward does, gdnsq_conv2d.py:80-84).
+        With `log_scale` (= log_wght_s) the kernels take the scale in the log domain and
+        return d/d log_wght_s directly; self.scale is then materialised lazily.
+        Returns (weight_q, row_min, row_max)."""
+        pshape = (weight.shape[0],) + (1,) * (weight.dim() - 1)
+        if log_scale is not None:
+            wq, mn, mx = ops.weight_fake_quant_log(weight, log_scale, method=self._method(), noise=noise)
+            zp = mn.view(pshape)
+            self.defer(lambda: (torch.exp2(log_scale).reshape(pshape), zp, self._min_val, self._max_val))
+        else:
+            wq, mn, mx = ops.weight_fake_quant(weight, self.scale, method=self._method(), noise=noise)
+            self.zero_point = mn.view(pshape)
         return wq, mn, mx
 
     def fake_quant_eval(self, value):

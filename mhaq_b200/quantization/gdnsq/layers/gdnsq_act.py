@@ -10,6 +10,7 @@ is one fused kernel each way.
 import torch
 from torch import nn, inf
 
+from .... import ops
 from ..gdnsq import Quantizer
 from ..gdnsq_utils import QNMethod
 
@@ -31,17 +32,23 @@ class NoisyAct(nn.Module):
         self.Q = Quantizer(self, torch.exp2(self._log_act_s), 0, -inf, inf, qnmethod=qnmethod)
         self.bw = torch.tensor(0.0)
 
+    def _operands(self):
+        """(scale, zero_point, min_val, max_val) exactly as the reference assigns them
+        (gdnsq_act.py:42-48)."""
+        s = torch.exp2(self.log_act_s)
+        q = torch.exp2(self.log_act_q)
+        return s, self.act_b, self.act_b, self.act_b + q - s
+
     def forward(self, x):
         if self.disable:
             return x
-        s = torch.exp2(self.log_act_s)
-        q = torch.exp2(self.log_act_q)
-
-        self.Q.zero_point = self.act_b
-        self.Q.min_val = self.act_b
-        self.Q.max_val = self.act_b + q - s
-        self.Q.scale = s
-
+        if self.training and self.Q.positive_scale and x.is_cuda:
+            # fused: the kernels read log_act_s / log_act_q / act_b themselves and return the
+            # log-domain gradients; Q.scale & co. are materialised only if somebody reads them
+            self.Q.defer(self._operands)
+            return ops.act_fake_quant(x, self.log_act_s, self.log_act_q, self.act_b,
+                                      method=self.Q._method())
+        self.Q.scale, self.Q.zero_point, self.Q.min_val, self.Q.max_val = self._operands()
         if self.training:
             return self.Q.fake_quant(x)
         # eval: the reference quantizes, asserts (3 host syncs), takes aminmax of the codes and

@@ -58,14 +58,15 @@ class NoisyConv2d(nn.Conv2d):
                                          torch.is_grad_enabled(), self.training)
         if hit is not None:
             return hit
-        s = torch.exp2(self.log_wght_s)
-        self.Q.scale = s
         mx = None
         if self.qscheme == QScheme.PER_CHANNEL and self.positive_scale_ok():
-            # fused: row min (zero point) + row max in one pass, quantization in the next
-            weight, mn_flat, mx = self.Q.fake_quant_weight(self.weight)
-            mn = self.Q.zero_point
+            # fused: row min (zero point) + row max in one pass, quantization in the next, the
+            # scale taken in the log domain (no exp2 / Exp2Backward launches)
+            weight, mn_flat, mx = self.Q.fake_quant_weight(self.weight, log_scale=self.log_wght_s)
+            s = mn = None
         else:
+            s = torch.exp2(self.log_wght_s)
+            self.Q.scale = s
             if self.qscheme == QScheme.PER_CHANNEL:
                 mn = self.weight.amin((1, 2, 3), keepdim=True)
             else:
@@ -75,6 +76,8 @@ class NoisyConv2d(nn.Conv2d):
             weight = self.Q.fake_quant(self.weight)
 
         if self.quant_bias:
+            if s is None:
+                s, mn = self.Q.scale, self.Q.zero_point
             self.Q_b.scale = s.ravel()
             self.Q_b.zero_point = mn.ravel()
             bias = self.Q_b.fake_quant(self.bias)

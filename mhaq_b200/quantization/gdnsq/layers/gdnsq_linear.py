@@ -49,10 +49,10 @@ class NoisyLinear(nn.Linear):
         if hit is not None:
             return hit
         if self.qscheme == QScheme.PER_CHANNEL:
-            self.Q.scale = torch.exp2(self.log_wght_s).reshape(self.out_features, 1)
             if self.Q.positive_scale and self.weight.is_cuda:
-                out = self.Q.fake_quant_weight(self.weight)
+                out = self.Q.fake_quant_weight(self.weight, log_scale=self.log_wght_s)
             else:
+                self.Q.scale = torch.exp2(self.log_wght_s).reshape(self.out_features, 1)
                 self.Q.zero_point = self.weight.amin(1, keepdim=True)
                 out = (self.Q.fake_quant(self.weight), None, None)
         else:

@@ -27,7 +27,7 @@ def test_header_symbols_all_exported():
 
 def test_abi_version_and_info():
     from mhaq_b200 import _lib
-    assert _lib.lib.mhaq_fq_abi_version() == 2
+    assert _lib.lib.mhaq_fq_abi_version() == 3
     assert b"sm_100a" in _lib.lib.mhaq_fq_build_info()
 
 
@@ -51,17 +51,22 @@ def test_argument_errors_without_gpu():
     from mhaq_b200 import _lib
     L = _lib.lib
     # null x / scale -> MHAQ_FQ_ENULL before anything touches CUDA
-    assert L.mhaq_fq_fwd_f32(None, None, None, None, None, None, None, 0, 0, 0, 0, 1, 8, 1, None, None) == -2
+    assert L.mhaq_fq_fwd_f32(None, None, None, None, None, None, None, 0, 0, 0, 0, 0, 1, 8, 1, None, None) == -2
     dummy = ctypes.c_void_p(16)
     # bad stride
-    assert L.mhaq_fq_fwd_f32(dummy, dummy, None, dummy, dummy, None, None, 2, 0, 0, 0, 1, 8, 1, None, None) == -1
+    assert L.mhaq_fq_fwd_f32(dummy, dummy, None, dummy, dummy, None, None, 2, 0, 0, 0, 0, 1, 8, 1, None, None) == -1
     # rows not divisible by channels
-    assert L.mhaq_fq_fwd_f32(dummy, dummy, None, dummy, dummy, None, None, 1, 1, 0, 0, 5, 8, 2, None, None) == -1
+    assert L.mhaq_fq_fwd_f32(dummy, dummy, None, dummy, dummy, None, None, 1, 1, 0, 0, 0, 5, 8, 2, None, None) == -1
+    # unknown parameter mode; ACT_LOG without log_act_q; ACT_LOG with channels
+    assert L.mhaq_fq_fwd_f32(dummy, dummy, None, dummy, dummy, None, None, 0, 0, 0, 0, 7, 1, 8, 1, None, None) == -1
+    assert L.mhaq_fq_fwd_f32(dummy, dummy, None, dummy, dummy, None, None, 0, 0, 0, 0, 1, 1, 8, 1, None, None) == -2
+    assert L.mhaq_fq_fwd_f32(dummy, dummy, None, dummy, dummy, dummy, None, 0, 0, 0, 0, 1, 2, 8, 2, None, None) == -1
     # bad method
-    assert L.mhaq_fq_bwd_f32(dummy, dummy, dummy, dummy, dummy, None, None, 0, 0, 0, 0, 1, 8, 1, 9, 0,
+    assert L.mhaq_fq_bwd_f32(dummy, dummy, dummy, dummy, dummy, None, None, 0, 0, 0, 0, 0, 1, 8, 1, 9, 0,
                              None, 0, 0, None, None, dummy, None) == -1
     # missing tickets buffer
-    assert L.mhaq_fq_bwd_finalize_f32(dummy, None, 1, 8, 1, None, None, None, None, None) == -2
+    assert L.mhaq_fq_bwd_finalize_f32(dummy, None, None, None, None, None, 0, 0, 0, 0, 0, 1, 8, 1, None, None, None,
+                                      None, None) == -2
     with pytest.raises(RuntimeError, match="EINVAL"):
         _lib.check(-1, "x")
 

@@ -267,3 +267,76 @@ def test_noisy_linear_matches_oracle(scheme):
     assert_bit_exact(lin.quantized_weight(), wq, "wq")
     torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=1e-4)    # GEMM: TF32 vs fp32
     assert_close_rel(lin.weight.grad, w.grad, 1e-3, "g_weight", abs_floor=2e-3)
+
+
+@pytest.mark.parametrize("signed", [True, False])
+def test_log_domain_activation_path_equals_linear_path(signed):
+    """MHAQ_FQ_PARAMS_ACT_LOG (kernels read log_act_s/log_act_q/act_b) vs the linear path fed
+    with torch's own exp2 / add / sub on the same device: outputs and input gradients bitwise,
+    log-domain gradients within 1e-5 of autograd's chain."""
+    import mhaq_b200
+    from mhaq_b200 import ops
+    torch.manual_seed(8)
+    x = torch.randn(6, 32, 28, 28, device="cuda") * 1.5
+    if not signed:
+        x = x.relu()
+    go = torch.randn_like(x)
+    for ls0, lq0, b0 in ((-2.37, 1.61, -1.93 if signed else 0.0), (-5.113, 2.0, -3.3 if signed else 0.0),
+                         (0.731, 1.9, -1.0 if signed else 0.0)):
+        def params():
+            return (torch.tensor([ls0], device="cuda", requires_grad=True),
+                    torch.tensor([lq0], device="cuda", requires_grad=True),
+                    torch.tensor([b0], device="cuda", requires_grad=signed))
+        ls, lq, b = params()
+        xa = x.clone().requires_grad_(True)
+        ya = ops.act_fake_quant(xa, ls, lq, b, method="STE", philox=(3, 9))
+        ya.backward(go)
+        ls2, lq2, b2 = params()
+        xb = x.clone().requires_grad_(True)
+        s, q = torch.exp2(ls2), torch.exp2(lq2)
+        yb = mhaq_b200.fake_quant(xb, s, b2, b2, b2 + q - s, method="STE", philox=(3, 9))
+        yb.backward(go)
+        assert torch.equal(ya, yb), "exp2f in-kernel must reproduce torch.exp2's bits"
+        assert torch.equal(xa.grad, xb.grad)
+        assert_close_rel(ls.grad, ls2.grad, 1e-5, "g_log_act_s", abs_floor=1e-6)
+        assert_close_rel(lq.grad, lq2.grad, 1e-5, "g_log_act_q", abs_floor=1e-6)
+        if signed:
+            assert_close_rel(b.grad, b2.grad, 1e-5, "g_act_b", abs_floor=1e-6)
+        else:
+            assert b.grad is None
+
+
+@pytest.mark.parametrize("method", ["STE", "LSQ", "AEWGS"])
+def test_log_domain_weight_path_equals_linear_path(method):
+    from mhaq_b200 import ops
+    torch.manual_seed(9)
+    w = torch.randn(48, 24, 3, 3, device="cuda") * 0.2
+    go = torch.randn_like(w)
+    log_s0 = (torch.rand(48, 1, 1, 1, device="cuda") * 2 - 5.3)
+    r = torch.randint(0, 2, w.shape, device="cuda").float() - 0.5
+    noise = None if method == "LSQ" else r
+    wa = w.clone().requires_grad_(True); la = log_s0.clone().requires_grad_(True)
+    qa, mna, mxa = ops.weight_fake_quant_log(wa, la, method=method, noise=noise)
+    (qa * go).sum().backward()
+    wb = w.clone().requires_grad_(True); lb = log_s0.clone().requires_grad_(True)
+    qb, mnb, mxb = ops.weight_fake_quant(wb, torch.exp2(lb), method=method, noise=noise)
+    (qb * go).sum().backward()
+    assert torch.equal(qa, qb) and torch.equal(mna, mnb) and torch.equal(mxa, mxb)
+    assert_close_rel(wa.grad, wb.grad, 1e-6, "g_weight", abs_floor=1e-7)
+    assert_close_rel(la.grad, lb.grad, 1e-5, "g_log_wght_s", abs_floor=1e-6)
+
+
+def test_quantizer_operands_materialise_lazily():
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_act import NoisyAct
+    act = NoisyAct(signed=True).cuda()
+    with torch.no_grad():
+        act.log_act_s.fill_(-2.5); act.log_act_q.fill_(1.5); act.act_b.fill_(-1.25)
+    act.train()
+    act(torch.randn(4, 8, 8, 8, device="cuda"))
+    assert act.Q._lazy is not None                      # nothing was computed for the fused call
+    s = act.Q.scale                                     # ... until somebody asks
+    assert act.Q._lazy is None and torch.equal(s, torch.exp2(act.log_act_s))
+    assert torch.equal(act.Q.max_val, act.act_b + torch.exp2(act.log_act_q) - s)
+    assert act.Q.zero_point is act.act_b and act.Q.min_val is act.act_b
+    act.Q.scale = torch.tensor([0.5], device="cuda")    # explicit assignment still works
+    assert float(act.Q.scale) == 0.5

@@ -414,8 +414,8 @@ def test_no_out_of_bounds_writes(fq, rows, inner):
         ops.check(ops.lib.mhaq_fq_bwd_f32(go.data_ptr(), x.data_ptr(), gx.data_ptr(), *L.params(),
                                           geo.n_rows, geo.n_inner, geo.n_ch, 0, 0, None, 1, 2, None, None,
                                           ws.data_ptr(), st), "bwd")
-        ops.check(ops.lib.mhaq_fq_bwd_finalize_f32(ws.data_ptr(), tk.data_ptr(), geo.n_rows, geo.n_inner,
-                                                   geo.n_ch, out[0].data_ptr(), out[1].data_ptr(),
+        ops.check(ops.lib.mhaq_fq_bwd_finalize_f32(ws.data_ptr(), tk.data_ptr(), *L.params(), geo.n_rows,
+                                                   geo.n_inner, geo.n_ch, out[0].data_ptr(), out[1].data_ptr(),
                                                    out[2].data_ptr(), out[3].data_ptr(), st), "fin")
         torch.cuda.synchronize()
         for name, buf in (("y", yb), ("codes", cb), ("gx", gxb), ("x", xb), ("go", gb)):
