@@ -60,6 +60,11 @@ def parse_args():
                          "buffer broadcast every step) instead of the lean wrapping")
     ap.add_argument("--graph", action="store_true",
                     help="QAT leg: capture the whole training step in a CUDA graph (single GPU)")
+    ap.add_argument("--nchw", dest="channels_last", action="store_false",
+                    help="QAT leg: keep model and batch in row-major NCHW (the reference Trainer's layout). "
+                         "Default is torch.channels_last (NHWC): cuDNN's Blackwell convolution / batch-norm "
+                         "kernels are NHWC-native (NCHW costs ~8 ms of layout transposes and 2x slower BN per "
+                         "step), and the fake-quant kernels walk dense NHWC storage directly, no copies")
     ap.add_argument("--no-eager-ref", action="store_true",
                     help="skip timing the reference's ATen chain on the GPU (second denominator)")
     return ap.parse_args()
@@ -188,8 +193,11 @@ class _EagerReferenceBackend:
 
     def __enter__(self):
         from mhaq_b200.quantization.gdnsq import gdnsq as G
+        from mhaq_b200 import ops
         from oracle import fq_oracle as O
-        self.G, self.saved = G, (G.Quantizer.fake_quant, G.Quantizer.fake_quant_eval)
+        self.G, self.ops = G, ops
+        self.saved = (G.Quantizer.fake_quant, G.Quantizer.fake_quant_eval, G.Quantizer.fake_quant_weight,
+                      ops.act_fake_quant)
 
         def fake_quant(q, value, noise=None):
             return O.fake_quant(value, q.scale, q.zero_point, q.min_val, q.max_val,
@@ -201,11 +209,28 @@ class _EagerReferenceBackend:
             return O.dequantize(codes, q.scale, q.zero_point), torch.stack(
                 [mm.min, mm.max, torch.zeros((), device=value.device)])
 
+        def fake_quant_weight(q, weight, log_scale=None, noise=None):
+            # NoisyConv2d.forward's weight lines (gdnsq_conv2d.py:72-84,98) op for op; no row
+            # range is returned, so ModelHelper re-reduces the weight like the reference does
+            if log_scale is not None:
+                q.scale = torch.exp2(log_scale)
+            q.zero_point = weight.amin(tuple(range(1, weight.dim())), keepdim=True)
+            wq = O.fake_quant(weight, q.scale, q.zero_point, -math.inf, math.inf,
+                              method=q.qnmethod.name, noise=noise)
+            return wq, None, None
+
+        def act_fake_quant(x, log_act_s, log_act_q, act_b, method="STE", noise=None, philox=None):
+            return O.act_fake_quant(x, log_act_s, log_act_q, act_b, noise=noise, method=method)
+
         G.Quantizer.fake_quant, G.Quantizer.fake_quant_eval = fake_quant, fake_quant_eval
+        G.Quantizer.fake_quant_weight = fake_quant_weight
+        ops.act_fake_quant = act_fake_quant
         return self
 
     def __exit__(self, *a):
-        self.G.Quantizer.fake_quant, self.G.Quantizer.fake_quant_eval = self.saved
+        G = self.G
+        (G.Quantizer.fake_quant, G.Quantizer.fake_quant_eval, G.Quantizer.fake_quant_weight,
+         self.ops.act_fake_quant) = self.saved
 
 
 def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
@@ -224,6 +249,11 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     q = harness.build_qat(a.qat_model, dev, qnmethod=a.qat_method, act_bit=a.qat_bits,
                           weight_bit=a.qat_bits, distillation=True, num_classes=classes,
                           calib_batch=x[: min(B, 64)])
+    if a.channels_last:
+        q.model.to(memory_format=torch.channels_last)
+        if getattr(q, "tmodel", None) is not None:
+            q.tmodel.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
     if use_dist:
         q.model = harness.wrap_ddp(q.model, dev, lean=not a.ddp_reference_flags)
     graphed = None
@@ -233,7 +263,7 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     else:
         opt = q.configure_optimizers()
     q.train(); q.wrapped_criterion.train(); q.tmodel.eval()
-    hx = x.cpu().pin_memory(); ht = t.cpu().pin_memory()
+    hx = x.cpu().pin_memory(); ht = t.cpu().pin_memory()      # (keeps x's memory format)
     hloss = torch.empty((), dtype=torch.float32).pin_memory()
 
     def step():
@@ -263,7 +293,7 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     ms_e = time_region(step_e2e, max(3, k // 2), use_dist) / max(3, k // 2)
     cfg = "configs[3] ResNet-18 224x224" if a.qat_model == "resnet18" else "configs[2] ResNet-20 32x32 (CIFAR-100 shaped)"
     res = {"workload": f"{cfg} {a.qat_method} W{a.qat_bits}A{a.qat_bits} QAT, distillation, RAdam, fp32/TF32, "
-                       f"batch {B}/GPU, {'DDP dp%d' % world if use_dist else 'single GPU'}"
+                       f"batch {B}/GPU, {'channels_last, ' if a.channels_last else ''}{'DDP dp%d' % world if use_dist else 'single GPU'}"
                        f"{', whole step replayed from a CUDA graph' if graphed is not None else ''}",
            "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
            "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1), "n_gpus": world,
@@ -445,12 +475,17 @@ def run_ours(a):
         if not a.no_eager_ref:
             out["reference_eager_gpu"] = eager_reference_leg(a, dev)
             if not a.no_resnet and not use_dist:
-                with _EagerReferenceBackend():
-                    rr = resnet18_leg(a, dev, 1, 0, False, profile_share=False)
-                out["reference_eager_gpu"]["resnet18_w4a4_qat"] = {
-                    "img_per_s": rr["img_per_s"], "ms_per_step": rr["ms_per_step"],
-                    "what": "same QAT step with every fake-quant routed through the reference's eager "
-                            "ATen chain on this GPU"}
+                key = "resnet18_w4a4_qat"
+                for cl in ((False, True) if a.channels_last else (False,)):
+                    b = argparse.Namespace(**vars(a))
+                    b.channels_last, b.graph = cl, False
+                    with _EagerReferenceBackend():
+                        rr = resnet18_leg(b, dev, 1, 0, False, profile_share=False)
+                    out["reference_eager_gpu"][key + ("_channels_last" if cl else "")] = {
+                        "img_per_s": rr["img_per_s"], "ms_per_step": rr["ms_per_step"],
+                        "what": "same QAT step with every fake-quant routed through the reference's eager "
+                                "ATen chain on this GPU, " + ("channels_last like our leg" if cl else
+                                "row-major NCHW as the reference's Trainer runs it")}
         if not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, steps=5, warmup=2)
         if a.sweep:

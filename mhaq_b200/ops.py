@@ -53,6 +53,50 @@ def _require_cuda(x: torch.Tensor) -> None:
         raise RuntimeError(f"mhaq_b200 fake-quant is fp32 only, got {x.dtype}")
 
 
+def _is_dense(x: torch.Tensor, axis: Optional[int]) -> bool:
+    """True if the kernels can walk x's storage directly as [n_rows][n_inner]: row-major, or
+    channels_last (NHWC / NDHWC strides) when the parameters are per-tensor (any dense
+    permutation is one flat row) or per dim-0 channel (each dim-0 slice is still one dense
+    block of numel/shape[0] elements).  cuDNN's fast convolution kernels want channels_last
+    activations; taking them as they are avoids a layout copy either side of every quantizer."""
+    if x.is_contiguous():
+        return True
+    if axis not in (None, 0):
+        return False
+    if x.dim() == 4:
+        return x.is_contiguous(memory_format=torch.channels_last)
+    if x.dim() == 5:
+        return x.is_contiguous(memory_format=torch.channels_last_3d)
+    return False
+
+
+def _dense(x: torch.Tensor, axis: Optional[int]) -> torch.Tensor:
+    return x if _is_dense(x, axis) else x.contiguous()
+
+
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    """[rows = shape[0], inner] view of a tensor that is dense per dim-0 slice, in storage order."""
+    rows = t.shape[0]
+    if t.is_contiguous():
+        return t.view(rows, -1)
+    inner = t.numel() // rows
+    return t.as_strided((rows, inner), (inner, 1))
+
+
+def _unrows(t2d: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """Inverse of _rows2d: a [rows, inner] storage-order result seen with `like`'s shape/strides."""
+    if like.is_contiguous():
+        return t2d.view_as(like)
+    return t2d.as_strided(like.shape, like.stride())
+
+
+def _like_layout(t: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """`t` (same shape as x) in x's memory layout, copying only if the strides differ."""
+    if t.stride() == x.stride():
+        return t
+    return torch.empty_like(x).copy_(t)
+
+
 class Geometry:
     """[n_rows][n_inner] view of a tensor and the channel layout of its parameters."""
 
@@ -294,7 +338,7 @@ def allreduce_packed_stats(stats: torch.Tensor) -> torch.Tensor:
 def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_gx: bool,
                    philox=None):
     geo = L.geo
-    go = go.contiguous()
+    go = _like_layout(go, x)
     gx = torch.empty_like(x) if need_gx else None
     n_ch = geo.n_ch
     if x.numel() == 0:
@@ -307,9 +351,9 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
     seed = offset = 0
     pdev = None
     if noise is not None:
-        noise = noise.contiguous()
         if noise.shape != x.shape or noise.dtype != torch.float32 or not noise.is_cuda:
             raise RuntimeError("explicit noise must be an fp32 CUDA tensor shaped like the input")
+        noise = _like_layout(noise, x)
     elif method != METHOD_IDS["LSQ"]:
         if philox is not None:
             seed, offset = philox
@@ -360,8 +404,9 @@ class _FakeQuantFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, scale, zp, lo, hi, method, noise, philox, code_only):
-        x = x.contiguous()
         L = _Launch(x, scale, zp, lo, hi)
+        # (per-tensor AEWGS re-views the tensor along dim 0, reference quirk 9: row-major only)
+        x = x.contiguous() if method == METHOD_IDS["AEWGS"] and L.geo.axis is None else _dense(x, L.geo.axis)
         y, codes, _ = _forward_impl(x, L, want_y=not code_only, want_codes=code_only,
                                     want_minmax=False)
         prm = (scale, zp, lo, hi)
@@ -421,9 +466,9 @@ def quantize_eval(x, scale, zero_point, min_val=None, max_val=None, want_y=True,
     """No-grad forward that also returns (min code, max code, #non-finite codes) as a
     3-element CUDA tensor — the eval-mode extras of gdnsq.py:211-217 / gdnsq_act.py:51-54
     in the same pass."""
-    x = x.detach().contiguous()
+    x = x.detach()
     L = _Launch(x, scale, zero_point, min_val, max_val)
-    return _forward_impl(x, L, want_y, want_codes, True)
+    return _forward_impl(_dense(x, L.geo.axis), L, want_y, want_codes, True)
 
 
 def philox_noise(shape_like: torch.Tensor, scale_like=None, seed: int = 0, offset: int = 0):
@@ -476,10 +521,9 @@ class _WeightFakeQuantFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, w, scale, method, noise, philox):
         ctx.set_materialize_grads(False)
-        w = w.contiguous()
+        w = _dense(w, 0)
         rows = w.shape[0]
-        w2 = w.view(rows, -1)
-        mn, mx, cmn, cmx = row_stats(w2)
+        mn, mx, cmn, cmx = row_stats(_rows2d(w))
         pshape = (rows,) + (1,) * (w.dim() - 1)
         L = _Launch(w, scale, mn.view(pshape), None, None)
         wq, _, _ = _forward_impl(w, L, True, False, False)
@@ -490,26 +534,26 @@ class _WeightFakeQuantFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_wq, g_mn, g_mx):
         w, scale, mn, mx, cmn, cmx = ctx.saved_tensors
-        rows = w.shape[0]
-        w2 = w.view(rows, -1)
+        w2 = _rows2d(w)
         g_scale = None
         if g_wq is not None:
             L = _Launch(w, scale, mn.view(ctx.pshape), None, None)
             gx, out = _backward_impl(g_wq, w, L, ctx.method, False, ctx.noise, True, ctx.philox)
             g_scale = _reduce_to_param(out[0], scale, L.geo, w.shape)
             g_min = out[1] if g_mn is None else out[1] + g_mn
-            gx2 = gx.view(rows, -1)
+            gx2 = _rows2d(gx)
         else:
             gx2, g_min = None, g_mn
         if not ctx.needs_input_grad[0]:
             return None, g_scale, None, None, None
         if g_min is None and g_mx is None:
-            gw = torch.zeros_like(w) if gx2 is None else gx2.view_as(w)
+            gw = torch.zeros_like(w) if gx2 is None else _unrows(gx2, w)
         else:
             gw = row_stats_backward(gx2, w2, mn if g_min is not None else None,
                                     cmn if g_min is not None else None, g_min,
                                     mx if g_mx is not None else None,
-                                    cmx if g_mx is not None else None, g_mx).view_as(w)
+                                    cmx if g_mx is not None else None, g_mx)
+            gw = _unrows(gw, w)
         return gw, (g_scale if ctx.needs_input_grad[1] else None), None, None, None
 
 
@@ -529,7 +573,7 @@ class _ActFakeQuantFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, log_act_s, log_act_q, act_b, method, noise, philox):
-        x = x.contiguous()
+        x = _dense(x, None)
         L = _Launch.act_log(x, log_act_s, log_act_q, act_b)
         y, _, _ = _forward_impl(x, L, True, False, False)
         ctx.save_for_backward(x, log_act_s, log_act_q, act_b)
@@ -560,9 +604,9 @@ class _WeightLogFakeQuantFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, w, log_wght_s, method, noise, philox):
         ctx.set_materialize_grads(False)
-        w = w.contiguous()
+        w = _dense(w, 0)
         rows = w.shape[0]
-        mn, mx, cmn, cmx = row_stats(w.view(rows, -1))
+        mn, mx, cmn, cmx = row_stats(_rows2d(w))
         L = _Launch.weight_log(w, log_wght_s, mn)
         wq, _, _ = _forward_impl(w, L, True, False, False)
         ctx.save_for_backward(w, log_wght_s, mn, mx, cmn, cmx)
@@ -572,25 +616,25 @@ class _WeightLogFakeQuantFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_wq, g_mn, g_mx):
         w, log_wght_s, mn, mx, cmn, cmx = ctx.saved_tensors
-        rows = w.shape[0]
-        w2 = w.view(rows, -1)
+        w2 = _rows2d(w)
         g_log_s = None
         if g_wq is not None:
             gx, out = _backward_impl(g_wq, w, ctx.L, ctx.method, False, ctx.noise, True, ctx.philox)
             g_log_s = out[0].reshape(log_wght_s.shape)
             g_min = out[1] if g_mn is None else out[1] + g_mn
-            gx2 = gx.view(rows, -1)
+            gx2 = _rows2d(gx)
         else:
             gx2, g_min = None, g_mn
         if not ctx.needs_input_grad[0]:
             return None, g_log_s, None, None, None
         if g_min is None and g_mx is None:
-            gw = torch.zeros_like(w) if gx2 is None else gx2.view_as(w)
+            gw = torch.zeros_like(w) if gx2 is None else _unrows(gx2, w)
         else:
             gw = row_stats_backward(gx2, w2, mn if g_min is not None else None,
                                     cmn if g_min is not None else None, g_min,
                                     mx if g_mx is not None else None,
-                                    cmx if g_mx is not None else None, g_mx).view_as(w)
+                                    cmx if g_mx is not None else None, g_mx)
+            gw = _unrows(gw, w)
         return gw, (g_log_s if ctx.needs_input_grad[1] else None), None, None, None
 
 

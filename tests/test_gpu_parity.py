@@ -472,3 +472,77 @@ def test_host_streaming_api_matches_device_api(fq, shape, per_channel, clip):
     for k, p in zip(("scale", "zero_point", "min_val", "max_val"), Pd):
         if p is not None:
             H.assert_close_rel(grads[k], p.grad, 1e-5, k, abs_floor=1e-5)
+
+
+# ---------------------------------------------------------------------------
+# channels_last (NHWC) tensors are walked in storage order, without layout copies
+# ---------------------------------------------------------------------------
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last if t.dim() == 4 else torch.channels_last_3d)
+
+
+@pytest.mark.parametrize("shape", [(4, 16, 9, 7), (2, 3, 5, 5), (8, 16, 56, 56), (2, 4, 3, 6, 5)])
+@pytest.mark.parametrize("go_layout", ["same", "row_major"])
+def test_channels_last_activation_equals_row_major(fq, shape, go_layout):
+    """Per-tensor parameters: a channels_last activation is quantized in place (output and input
+    gradient keep the NHWC strides) and every element gets exactly the row-major result."""
+    x, go, r, scale, zp, lo, hi, mk = _leafs(shape, False, 4, True, 23, "cuda")
+    y0, gx0, g0 = _run(fq.fake_quant, x, go, r, scale, zp, lo, hi, mk, "STE", "cuda")
+    xs = _cl(x.cuda()).requires_grad_(True)
+    P = [mk(p) for p in (scale, zp, lo, hi)]
+    y = fq.fake_quant(xs, *P, method="STE", noise=_cl(r.cuda()))
+    assert y.stride() == xs.stride()
+    y.backward(_cl(go.cuda()) if go_layout == "same" else go.cuda())
+    assert xs.grad.stride() == xs.stride()
+    H.assert_bit_exact(y, y0, "y")
+    H.assert_bit_exact(xs.grad, gx0, "gx")
+    for p, g, k in zip(P, g0, ("scale", "zp", "lo", "hi")):
+        H.assert_close_rel(p.grad, g, REL, k, abs_floor=2e-5)
+    # fused NoisyAct entry (log-domain parameters) on the same layout
+    ls = torch.tensor([-2.0], device="cuda", requires_grad=True)
+    lq = torch.tensor([2.0], device="cuda", requires_grad=True)
+    ab = torch.tensor([-2.0], device="cuda", requires_grad=True)
+    outs = []
+    for xin, gin in ((x.cuda(), go.cuda()), (_cl(x.cuda()), _cl(go.cuda()))):
+        for p in (ls, lq, ab):
+            p.grad = None
+        xin = xin.requires_grad_(True)
+        ya = fq.ops.act_fake_quant(xin, ls, lq, ab, method="LSQ")
+        ya.backward(gin)
+        assert ya.stride() == xin.stride() and xin.grad.stride() == xin.stride()
+        outs.append((ya.detach(), xin.grad, ls.grad.clone(), lq.grad.clone(), ab.grad.clone()))
+    H.assert_bit_exact(outs[1][0], outs[0][0], "act y")
+    H.assert_bit_exact(outs[1][1], outs[0][1], "act gx")
+    for i, k in ((2, "log_act_s"), (3, "log_act_q"), (4, "act_b")):
+        H.assert_close_rel(outs[1][i], outs[0][i], REL, k, abs_floor=2e-5)
+
+
+@pytest.mark.parametrize("shape,method", [((64, 64, 3, 3), "STE"), ((32, 50, 3, 3), "LSQ"),
+                                          ((16, 512, 3, 3), "AEWGS")])
+def test_channels_last_weight_equals_row_major(fq, shape, method):
+    """Per-channel (dim 0) weights in channels_last: each output channel is still one dense
+    block; row statistics, fake-quant, gradients and the amin scatter act on it in place."""
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(shape, generator=g).cuda()
+    go = torch.randn(shape, generator=g).cuda()
+    r = (torch.randint(0, 2, shape, generator=g).float() - 0.5).cuda()
+    log_s = (torch.full((shape[0], 1, 1, 1), -3.0) + 0.2 * torch.rand((shape[0], 1, 1, 1), generator=g)).cuda()
+    res = []
+    for conv in (lambda t: t, _cl):
+        wl = conv(w).clone(memory_format=torch.preserve_format).requires_grad_(True)
+        ls = log_s.clone().requires_grad_(True)
+        noise = None if method == "LSQ" else conv(r)
+        wq, mn, mx = fq.ops.weight_fake_quant_log(wl, ls, method=method, noise=noise)
+        assert wq.stride() == wl.stride()
+        loss = (wq * conv(go)).sum() + (mx - mn).sum()
+        loss.backward()
+        assert wl.grad.stride() == wl.stride()
+        res.append((wq.detach(), wl.grad, ls.grad, mn.detach(), mx.detach()))
+    H.assert_bit_exact(res[1][0], res[0][0], "wq")
+    H.assert_bit_exact(res[1][3], res[0][3], "row_min")
+    H.assert_bit_exact(res[1][4], res[0][4], "row_max")
+    if method == "AEWGS":
+        H.assert_close_rel(res[1][1], res[0][1], REL, "g_weight", abs_floor=2e-6)
+    else:
+        H.assert_close_rel(res[1][1], res[0][1], REL, "g_weight", abs_floor=2e-5)
+    H.assert_close_rel(res[1][2], res[0][2], REL, "g_log_wght_s", abs_floor=2e-5)
