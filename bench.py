@@ -58,8 +58,11 @@ def parse_args():
     ap.add_argument("--ddp-reference-flags", action="store_true",
                     help="wrap DDP exactly like the reference's Trainer (find_unused_parameters=True, "
                          "buffer broadcast every step) instead of the lean wrapping")
-    ap.add_argument("--graph", action="store_true",
-                    help="QAT leg: capture the whole training step in a CUDA graph (single GPU)")
+    ap.add_argument("--graph", action="store_true", default=True, help=argparse.SUPPRESS)
+    ap.add_argument("--no-graph", dest="graph", action="store_false",
+                    help="QAT leg: launch the training step eagerly from Python.  Default: the whole step "
+                         "(teacher+student forward, loss, backward, DDP all-reduces, RAdam) is captured "
+                         "once in a CUDA graph and replayed")
     ap.add_argument("--nchw", dest="channels_last", action="store_false",
                     help="QAT leg: keep model and batch in row-major NCHW (the reference Trainer's layout). "
                          "Default is torch.channels_last (NHWC): cuDNN's Blackwell convolution / batch-norm "
@@ -255,54 +258,32 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
             q.tmodel.to(memory_format=torch.channels_last)
         x = x.contiguous(memory_format=torch.channels_last)
     if use_dist:
-        q.model = harness.wrap_ddp(q.model, dev, lean=not a.ddp_reference_flags)
-    graphed = None
-    if a.graph and not use_dist:
-        graphed = harness.GraphedTrainStep(q, (x, t), seed=1234)
-        opt = graphed.opt
-    else:
-        opt = q.configure_optimizers()
+        wrap = harness.ddp_side_stream if a.graph else harness.wrap_ddp
+        q.model = wrap(q.model, dev, lean=not a.ddp_reference_flags)
     q.train(); q.wrapped_criterion.train(); q.tmodel.eval()
-    hx = x.cpu().pin_memory(); ht = t.cpu().pin_memory()      # (keeps x's memory format)
-    hloss = torch.empty((), dtype=torch.float32).pin_memory()
+    opt = q.configure_optimizers()
 
-    def step():
-        if graphed is not None:
-            return graphed()
-        loss = q.training_step((x, t), 0)
+    def eager_step(batch=None):
+        loss = q.training_step(batch or (x, t), 0)
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=True)
-        return loss
+        return loss.detach()
 
-    def step_e2e():
-        if graphed is not None:
-            hloss.copy_(graphed((hx, ht)), non_blocking=True)
-            return
-        xd = hx.to(dev, non_blocking=True); td = ht.to(dev, non_blocking=True)
-        loss = q.training_step((xd, td), 0)
-        loss.backward()
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-        hloss.copy_(loss.detach(), non_blocking=True)
-
-    for _ in range(4):
-        step()
+    res = {}
     k = a.resnet_steps
-    ms = time_region(step, k, use_dist) / k
-    ms_e = time_region(step_e2e, max(3, k // 2), use_dist) / max(3, k // 2)
-    cfg = "configs[3] ResNet-18 224x224" if a.qat_model == "resnet18" else "configs[2] ResNet-20 32x32 (CIFAR-100 shaped)"
-    res = {"workload": f"{cfg} {a.qat_method} W{a.qat_bits}A{a.qat_bits} QAT, distillation, RAdam, fp32/TF32, "
-                       f"batch {B}/GPU, {'channels_last, ' if a.channels_last else ''}{'DDP dp%d' % world if use_dist else 'single GPU'}"
-                       f"{', whole step replayed from a CUDA graph' if graphed is not None else ''}",
-           "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
-           "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1), "n_gpus": world,
-           "quantized_act_elems_per_step": (1680896 if a.qat_model == "resnet18" else 184320) * B}
-    if rank == 0 and not use_dist and profile_share and graphed is None:   # (a rank-local DDP step would dead-lock the other ranks)
-        try:   # share of the step spent in the fake-quant kernels (CUPTI kernel times)
+    if a.graph and not use_dist:
+        # the same step launched eagerly from Python first: its time, and (CUPTI) which share of
+        # the GPU time the fake-quant kernels take — a graph replay hides kernel names from CUPTI
+        for _ in range(4):
+            eager_step()
+        res["eager_ms_per_step"] = round(time_region(eager_step, k, False) / k, 2)
+    if rank == 0 and not use_dist and profile_share:   # (a rank-local DDP step would dead-lock the other ranks)
+        try:
             from torch.profiler import profile, ProfilerActivity
+            eager_step()
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                step(); step()
+                eager_step(); eager_step()
                 torch.cuda.synchronize()
             tot = fq = 0.0
             for ev in prof.key_averages():
@@ -313,13 +294,55 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
             if tot > 0:
                 res["fake_quant_kernel_share"] = round(fq / tot, 4)
                 res["fake_quant_ms_per_step"] = round(fq / 2 / 1e3, 3)
-                res["gpu_kernel_ms_per_step"] = round(tot / 2 / 1e3, 2)   # rest of the step = GPU idle
+                res["gpu_kernel_ms_per_step"] = round(tot / 2 / 1e3, 2)   # rest of an eager step = GPU idle
         except Exception as exc:   # profiler unavailable: the throughput numbers stand alone
             res["fake_quant_kernel_share"] = None
             res["profiler_error"] = str(exc)[:80]
+
+    graphed = None
+    if a.graph:
+        del opt
+        graphed = harness.GraphedTrainStep(q, (x, t), seed=1234 + rank)
+    step = graphed if graphed is not None else eager_step
+
+    # end to end: every step's batch comes from pinned host memory (H2D inside the timed region,
+    # double-buffered on a copy stream so the copy of batch k+1 overlaps step k) and the step's
+    # loss is read back to the host
+    hx = x.cpu().pin_memory(); ht = t.cpu().pin_memory()      # (keeps x's memory format)
+    hloss = torch.empty((), dtype=torch.float32).pin_memory()
+    feed = harness.BatchPrefetcher((x, t))
+    feed.put((hx, ht))
+
+    def step_e2e():
+        batch = feed.get()
+        feed.put((hx, ht))                  # next step's copy, in flight while this step computes
+        hloss.copy_(step(batch), non_blocking=True)
+        feed.release()
+
+    for _ in range(4):
+        step()
+    ms = time_region(step, k, use_dist) / k
+    ke = max(3, k // 2)
+    step_e2e()
+    ms_e = time_region(step_e2e, ke, use_dist) / ke
+    cfg = "configs[3] ResNet-18 224x224" if a.qat_model == "resnet18" else "configs[2] ResNet-20 32x32 (CIFAR-100 shaped)"
+    res = {"workload": f"{cfg} {a.qat_method} W{a.qat_bits}A{a.qat_bits} QAT, distillation, RAdam, fp32/TF32, "
+                       f"batch {B}/GPU, {'channels_last' if a.channels_last else 'NCHW'}, "
+                       f"{'DDP dp%d' % world if use_dist else 'single GPU'}, "
+                       f"{'whole step (NCCL all-reduces included) replayed from a CUDA graph' if graphed is not None else 'eager launches'}",
+           "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
+           "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1),
+           "e2e_h2d_bytes_per_step": hx.numel() * 4 + ht.numel() * 8, "n_gpus": world,
+           "quantized_act_elems_per_step": (1680896 if a.qat_model == "resnet18" else 184320) * B, **res}
+    if use_dist:   # replicas must hold identical parameters after the DDP steps
+        import torch.distributed as dist
+        chk = torch.stack([p.detach().double().sum() for p in q.model.parameters()]).sum().reshape(1)
+        lo_, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        res["ddp_replicas_in_sync"] = bool((lo_ == hi_).item())
     if graphed is not None:
         graphed.close()
-    del q, opt, graphed
+    del q, graphed, step, feed
     torch.cuda.empty_cache()
     return res
 
@@ -363,6 +386,8 @@ def run_ours(a):
     if use_dist:
         import torch.distributed as dist
         import datetime
+        if a.graph:   # torch's recipe for capturing DDP's NCCL all-reduces in a CUDA graph
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     n = 1 << a.log2n
     x, go, scale, zp, lo, hi = make_inputs(a, dev)
@@ -490,7 +515,7 @@ def run_ours(a):
             out["cpu_baseline"] = cpu_baseline(a, steps=5, warmup=2)
         if a.sweep:
             sweep(a, dev)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if use_dist:
         import torch.distributed as dist
         dist.barrier()
@@ -576,7 +601,7 @@ def run_reference(a):
             out["cpu_config0_step"] = cpu_config0_step()
         except Exception as exc:   # never let the extra leg break the contract line
             out["cpu_config0_step"] = {"error": str(exc)[:120]}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ---------------------------------------------------------------------------
@@ -644,8 +669,29 @@ def sweep(a, dev):
     json.dump({"peak_GBps": peak, "rows": rows}, open(os.path.join(ROOT, "gpurun_out", "sweep.json"), "w"), indent=1)
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """ONE JSON line on stdout: NCCL (NCCL_DEBUG=VERSION/INFO) and other native libraries print
+    to fd 1; keep a private copy of the real stdout for the JSON line and point fd 1 at stderr."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
     a = parse_args()
+    _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

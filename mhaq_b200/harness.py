@@ -203,6 +203,17 @@ def wrap_ddp(model: nn.Module, device, lean: bool = True):
                gradient_as_bucket_view=True)
 
 
+def ddp_side_stream(model: nn.Module, device, lean: bool = True):
+    """`wrap_ddp` executed on a side stream — what torch requires of a DDP module whose backward
+    (bucket all-reduces included) is later captured into a CUDA graph."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        wrapped = wrap_ddp(model, device, lean=lean)
+    torch.cuda.current_stream().wait_stream(side)
+    return wrapped
+
+
 def fit_steps(qmodel: LModule, batches, ddp: bool = False, device=None, on_step=None,
               sync_bn: bool = False):
     """Run the training steps in Lightning's order.  `batches`: iterable of (inputs, target).
@@ -226,19 +237,66 @@ def fit_steps(qmodel: LModule, batches, ddp: bool = False, device=None, on_step=
     return qmodel
 
 
+class BatchPrefetcher:
+    """Double-buffered host->device staging of training batches on a copy stream, so the PCIe
+    copy of batch k+1 overlaps the GPU work of step k (what a DataLoader with pinned memory and
+    `non_blocking` copies gives the reference's Trainer).  put() enqueues a copy into the free
+    slot; get() makes the current stream wait for the oldest filled slot and returns its device
+    tensors; release() marks that slot reusable once the current stream's work so far is done."""
+
+    def __init__(self, example_batch, depth: int = 2):
+        self.slots = [tuple(torch.empty_like(t) for t in example_batch) for _ in range(depth)]
+        self.stream = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event() for _ in range(depth)]
+        self.free = [torch.cuda.Event() for _ in range(depth)]
+        for ev in self.free:
+            ev.record()
+        self.head = self.tail = self.count = 0
+
+    def put(self, host_batch):
+        if self.count == len(self.slots):
+            raise RuntimeError("BatchPrefetcher: all slots are in flight")
+        i = self.head
+        self.head = (i + 1) % len(self.slots)
+        self.count += 1
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.free[i])
+            for d, h in zip(self.slots[i], host_batch):
+                d.copy_(h, non_blocking=True)
+            self.ready[i].record(self.stream)
+
+    def get(self):
+        if self.count == 0:
+            raise RuntimeError("BatchPrefetcher: nothing in flight")
+        torch.cuda.current_stream().wait_event(self.ready[self.tail])
+        return self.slots[self.tail]
+
+    def release(self):
+        self.free[self.tail].record()
+        self.tail = (self.tail + 1) % len(self.slots)
+        self.count -= 1
+
+
 class GraphedTrainStep:
     """One QAT training step (teacher + student forward, loss, backward, optimizer) captured
     in a CUDA graph and replayed — SURVEY.md §8 row (f)-4.  CIFAR-sized models are bound by
     host launch overhead (ResNet-20, batch 256: ~19 ms of Python/launch time for ~9 ms of GPU
-    work); a replay has none.  Single process / single GPU; the in-kernel noise reads a
-    device-resident Philox state that is advanced inside the graph, so every replay draws
-    fresh noise.  Host-side schedules (`wrapped_criterion.t`, learning-rate callbacks) are
+    work); a replay has none.  The in-kernel noise reads a device-resident Philox state that is
+    advanced inside the graph, so every replay draws fresh noise.  Under DDP (one process per
+    GPU) the bucketed gradient all-reduces — and AEWGS's packed statistics all-reduce — are
+    NCCL kernels captured into the same graph with their stream dependencies: wrap the model
+    with `wrap_ddp` on a side stream first (`ddp_side_stream`), the warm-up then runs the >= 11
+    eager DDP iterations torch asks for before a whole-backward capture.  Host-side schedules (`wrapped_criterion.t`, learning-rate callbacks) are
     frozen at capture time — re-capture after changing them."""
 
     STRIDE = 4096        # > number of quantizer backward calls per step
 
-    def __init__(self, qmodel: LModule, example_batch, seed: int = 0, warmup: int = 3):
+    def __init__(self, qmodel: LModule, example_batch, seed: int = 0, warmup: Optional[int] = None):
         from . import ops
+        import torch.distributed as dist
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if warmup is None:
+            warmup = 11 if self.distributed else 3
         x, t = example_batch
         self.ops, self.qmodel = ops, qmodel
         self.x, self.t = x.clone(), t.clone()
@@ -252,6 +310,7 @@ class GraphedTrainStep:
         if hasattr(qmodel, "wrapped_criterion"):
             qmodel.wrapped_criterion.train()
             qmodel.wrapped_criterion.make_capturable(dev)
+        self._release_autograd_state(qmodel)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -259,10 +318,39 @@ class GraphedTrainStep:
                 self._body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._release_autograd_state(qmodel)      # (the warm-up's graph lives on the side stream)
         self.graph = torch.cuda.CUDAGraph()
         self.opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
+        # (thread_local: NCCL's watchdog thread may query events while this thread captures)
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if self.distributed else "global"):
             self.loss = self._body()
+
+    @staticmethod
+    def _release_autograd_state(qmodel):
+        """Drop whatever still references the autograd graph of an earlier eager step: the
+        criterion keeps its last loss terms for logging (gdnsq_loss.py:60-66) and a layer may hold
+        a quantized weight whose backward never ran.  A live graph keeps its AccumulateGrad nodes —
+        bound to the stream of that eager step — and a captured backward may not synchronise
+        with a stream outside the capture."""
+        crit = getattr(qmodel, "wrapped_criterion", None)
+        if crit is not None:
+            for k, v in list(vars(crit).items()):
+                if torch.is_tensor(v) and v.grad_fn is not None:
+                    setattr(crit, k, v.detach())
+        for m in qmodel.modules():
+            cache = getattr(m, "_wq_cache", None)
+            if cache is not None:
+                cache.clear()
+            # the layers leave their last operands on the Quantizer (gdnsq_conv2d.py:80-84:
+            # `self.Q.zero_point = weight.amin(...)` carries that step's graph)
+            for name in ("Q", "Q_b"):
+                qz = m.__dict__.get(name)
+                if qz is not None and hasattr(qz, "_resolve"):
+                    qz._resolve()
+                    for attr in ("_scale", "_zero_point", "_min_val", "_max_val"):
+                        v = getattr(qz, attr, None)
+                        if torch.is_tensor(v) and v.grad_fn is not None:
+                            setattr(qz, attr, v.detach())
 
     def _body(self):
         self.ops.reset_philox_call_counter()

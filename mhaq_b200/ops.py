@@ -610,7 +610,10 @@ class _WeightLogFakeQuantFn(torch.autograd.Function):
         L = _Launch.weight_log(w, log_wght_s, mn)
         wq, _, _ = _forward_impl(w, L, True, False, False)
         ctx.save_for_backward(w, log_wght_s, mn, mx, cmn, cmx)
-        ctx.L, ctx.method, ctx.noise, ctx.philox = L, method, noise, philox
+        # (L references `mn`, an OUTPUT of this node: keeping it on ctx would tie the node to its
+        # own output — a cycle through C++ that Python's GC cannot see, i.e. a leaked graph whose
+        # AccumulateGrad nodes then outlive the step.  It is rebuilt in backward.)
+        ctx.method, ctx.noise, ctx.philox = method, noise, philox
         return wq, mn, mx
 
     @staticmethod
@@ -619,7 +622,8 @@ class _WeightLogFakeQuantFn(torch.autograd.Function):
         w2 = _rows2d(w)
         g_log_s = None
         if g_wq is not None:
-            gx, out = _backward_impl(g_wq, w, ctx.L, ctx.method, False, ctx.noise, True, ctx.philox)
+            L = _Launch.weight_log(w, log_wght_s, mn)
+            gx, out = _backward_impl(g_wq, w, L, ctx.method, False, ctx.noise, True, ctx.philox)
             g_log_s = out[0].reshape(log_wght_s.shape)
             g_min = out[1] if g_mn is None else out[1] + g_mn
             gx2 = _rows2d(gx)

@@ -224,6 +224,14 @@ def test_cuda_graph_training_step_replays_and_trains():
     x = torch.randn(64, 3, 32, 32, device=dev)
     t = torch.randint(0, 10, (64,), device=dev)
     q = harness.build_qat("resnet20", dev, qnmethod="STE", distillation=True, calib_batch=x, lr=1e-2)
+    # eager steps on the default stream first (the criterion keeps their loss terms, hence their
+    # autograd graph, alive): the capture must not inherit that stream
+    opt = q.configure_optimizers()
+    q.train(); q.wrapped_criterion.train()
+    for _ in range(2):
+        q.training_step((x, t), 0).backward()
+        opt.step(); opt.zero_grad(set_to_none=True)
+    del opt
     step = harness.GraphedTrainStep(q, (x, t), seed=5)
     try:
         base = int(step.state[1])
@@ -233,7 +241,7 @@ def test_cuda_graph_training_step_replays_and_trains():
         assert all(math.isfinite(v) for v in losses)
         assert not torch.equal(w0, q.model.layer1[0].conv1._modules["0"].weight.detach())
         cnt = q.wrapped_criterion.cnt
-        assert torch.is_tensor(cnt) and float(cnt) >= 5      # advanced inside the graph
+        assert torch.is_tensor(cnt) and float(cnt) >= 7      # advanced inside the graph
         # a new batch is copied into the static buffers
         x2 = torch.randn_like(x)
         l2 = float(step((x2, t)))
@@ -340,3 +348,54 @@ def test_quantizer_operands_materialise_lazily():
     assert act.Q.zero_point is act.act_b and act.Q.min_val is act.act_b
     act.Q.scale = torch.tensor([0.5], device="cuda")    # explicit assignment still works
     assert float(act.Q.scale) == 0.5
+
+
+def test_batch_prefetcher_delivers_batches_in_order():
+    """harness.BatchPrefetcher: double-buffered H2D staging used by the end-to-end bench leg."""
+    from mhaq_b200.harness import BatchPrefetcher
+    ex = (torch.empty(4, 3, 8, 8, device="cuda"), torch.empty(4, dtype=torch.long, device="cuda"))
+    feed = BatchPrefetcher(ex)
+    host = [(torch.full((4, 3, 8, 8), float(k)).pin_memory(), torch.full((4,), k).pin_memory())
+            for k in range(6)]
+    feed.put(host[0])
+    seen = []
+    for k in range(6):
+        xb, tb = feed.get()
+        if k + 1 < 6:
+            feed.put(host[k + 1])
+        seen.append((xb.sum().clone(), tb.sum().clone()))     # consume on the current stream
+        feed.release()
+    torch.cuda.synchronize()
+    for k, (sx, st) in enumerate(seen):
+        assert sx.item() == k * 4 * 3 * 8 * 8 and st.item() == 4 * k
+    with pytest.raises(RuntimeError):
+        feed.get()
+
+
+def test_autograd_functions_do_not_leak_their_graph():
+    """No reference cycle between an autograd node and its own outputs: once the outputs are
+    dropped (with or without a backward) the node and what it saved must be freed — a leaked
+    node keeps its AccumulateGrad nodes alive across steps, which breaks CUDA-graph capture."""
+    import gc
+    import weakref
+    from mhaq_b200 import ops
+    w = torch.randn(8, 4, 3, 3, device="cuda", requires_grad=True)
+    ls = torch.full((8, 1, 1, 1), -3.0, device="cuda", requires_grad=True)
+    x = torch.randn(2, 4, 6, 6, device="cuda", requires_grad=True)
+    la, lq, ab = (torch.tensor([v], device="cuda", requires_grad=True) for v in (-2.0, 2.0, -2.0))
+    for run_backward in (True, False):
+        outs = list(ops.weight_fake_quant_log(w, ls, method="LSQ"))
+        outs += list(ops.weight_fake_quant(w, torch.exp2(ls), method="LSQ"))
+        outs.append(ops.act_fake_quant(x, la, lq, ab, method="LSQ"))
+        outs.append(ops.fake_quant(x, torch.exp2(la), ab, ab, ab + 3.0, method="LSQ"))
+        refs = [weakref.ref(o) for o in outs]
+        for o in outs:
+            try:
+                refs.append(weakref.ref(o.grad_fn))
+            except TypeError:       # node type without weak-reference support
+                pass
+        if run_backward:
+            sum(o.sum() for o in outs).backward()
+        del outs, o
+        gc.collect()
+        assert all(r() is None for r in refs), "an autograd node or one of its outputs survived"
