@@ -172,6 +172,10 @@ CASES = [
     ((8, 40000), True, 5, True, "STE"),               # long rows: several tasks per row, clipped
     ((1, 70000), False, 6, False, "LSQ"),             # per-tensor, no clamp
     ((512,), False, 4, False, "STE"),
+    ((1, 50, 64, 256), False, 2, True, "STE"),        # RFDN-style activations (config 5), W2A2
+    ((4, 12, 41, 41), False, 2, True, "STE"),         # RFDN's 41x41 ESA maps: 80 688 elements, ragged
+    ((12, 12, 3, 3), True, 2, False, "LSQ"),          # RFDN's smallest weight: rows of 108
+    ((25, 50, 3, 3), True, 2, False, "LSQ"),
 ]
 
 
