@@ -50,9 +50,11 @@ def parse_args():
     ap.add_argument("--no-resnet", action="store_true", help="skip the ResNet-18 W4A4 QAT leg")
     ap.add_argument("--resnet-batch", type=int, default=256, help="per-GPU batch (config 4)")
     ap.add_argument("--resnet-steps", type=int, default=12)
-    ap.add_argument("--qat-model", default="resnet18", choices=["resnet18", "resnet20"],
+    ap.add_argument("--qat-model", default="resnet18", choices=["resnet18", "resnet20", "rfdn"],
                     help="resnet18 = configs[3] (ImageNet-shaped, STE W4A4); resnet20 = configs[2] "
-                         "(CIFAR-100-shaped; use --qat-method AEWGS --qat-bits 1)")
+                         "(CIFAR-100-shaped; use --qat-method AEWGS --qat-bits 1); rfdn = configs[4] "
+                         "(x4 super-resolution on 256x256 patches, L1, no teacher; use --qat-method LSQ "
+                         "--qat-bits 2 --resnet-batch 16)")
     ap.add_argument("--qat-method", default="STE", choices=["STE", "LSQ", "AEWGS", "EWGS"])
     ap.add_argument("--qat-bits", type=int, default=4)
     ap.add_argument("--ddp-reference-flags", action="store_true",
@@ -236,6 +238,12 @@ class _EagerReferenceBackend:
          self.ops.act_fake_quant) = self.saved
 
 
+def qat_key(a):
+    if (a.qat_model, a.qat_method, a.qat_bits) == ("resnet18", "STE", 4):
+        return "resnet18_w4a4_qat"
+    return f"{a.qat_model}_{a.qat_method.lower()}_w{a.qat_bits}a{a.qat_bits}_qat"
+
+
 def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     """BASELINE configs[3]: torchvision ResNet-18, ImageNet-shaped synthetic batch (256 per GPU,
     224x224), GDNSQ/STE W4A4 per-channel, distillation (Symmetrical KL) from a frozen FP copy,
@@ -246,12 +254,19 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     torch.set_float32_matmul_precision("high")
     B = a.resnet_batch
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    side, classes = (224, 1000) if a.qat_model == "resnet18" else (32, 100)
-    x = torch.randn(B, 3, side, side, device=dev, generator=g)
-    t = torch.randint(0, classes, (B,), device=dev, generator=g)
-    q = harness.build_qat(a.qat_model, dev, qnmethod=a.qat_method, act_bit=a.qat_bits,
-                          weight_bit=a.qat_bits, distillation=True, num_classes=classes,
-                          calib_batch=x[: min(B, 64)])
+    sr = a.qat_model == "rfdn"
+    if sr:      # LR patch in [0,1] (denormalised x255 inside the module), HR target x4
+        x = torch.rand(B, 3, 256, 256, device=dev, generator=g)
+        t = torch.rand(B, 3, 1024, 1024, device=dev, generator=g)
+        q = harness.build_qat("rfdn", dev, qnmethod=a.qat_method, act_bit=a.qat_bits, weight_bit=a.qat_bits,
+                              distillation=False, lr=5e-4, calib_batch=x[: min(B, 4)], calib_bits=a.qat_bits)
+    else:
+        side, classes = (224, 1000) if a.qat_model == "resnet18" else (32, 100)
+        x = torch.randn(B, 3, side, side, device=dev, generator=g)
+        t = torch.randint(0, classes, (B,), device=dev, generator=g)
+        q = harness.build_qat(a.qat_model, dev, qnmethod=a.qat_method, act_bit=a.qat_bits,
+                              weight_bit=a.qat_bits, distillation=True, num_classes=classes,
+                              calib_batch=x[: min(B, 64)])
     if a.channels_last:
         q.model.to(memory_format=torch.channels_last)
         if getattr(q, "tmodel", None) is not None:
@@ -260,7 +275,9 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     if use_dist:
         wrap = harness.ddp_side_stream if a.graph else harness.wrap_ddp
         q.model = wrap(q.model, dev, lean=not a.ddp_reference_flags)
-    q.train(); q.wrapped_criterion.train(); q.tmodel.eval()
+    q.train(); q.wrapped_criterion.train()
+    if getattr(q, "tmodel", None) is not None:
+        q.tmodel.eval()
     opt = q.configure_optimizers()
 
     def eager_step(batch=None):
@@ -325,15 +342,18 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     ke = max(3, k // 2)
     step_e2e()
     ms_e = time_region(step_e2e, ke, use_dist) / ke
-    cfg = "configs[3] ResNet-18 224x224" if a.qat_model == "resnet18" else "configs[2] ResNet-20 32x32 (CIFAR-100 shaped)"
-    res = {"workload": f"{cfg} {a.qat_method} W{a.qat_bits}A{a.qat_bits} QAT, distillation, RAdam, fp32/TF32, "
+    cfg = {"resnet18": "configs[3] ResNet-18 224x224", "resnet20": "configs[2] ResNet-20 32x32 (CIFAR-100 shaped)",
+           "rfdn": "configs[4] RFDN x4 SR, 256x256 LR patches, L1"}[a.qat_model]
+    res = {"workload": f"{cfg} {a.qat_method} W{a.qat_bits}A{a.qat_bits} QAT, {'no teacher' if sr else 'distillation'}, RAdam, fp32/TF32, "
                        f"batch {B}/GPU, {'channels_last' if a.channels_last else 'NCHW'}, "
                        f"{'DDP dp%d' % world if use_dist else 'single GPU'}, "
                        f"{'whole step (NCCL all-reduces included) replayed from a CUDA graph' if graphed is not None else 'eager launches'}",
            "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
            "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1),
-           "e2e_h2d_bytes_per_step": hx.numel() * 4 + ht.numel() * 8, "n_gpus": world,
-           "quantized_act_elems_per_step": (1680896 if a.qat_model == "resnet18" else 184320) * B, **res}
+           "e2e_h2d_bytes_per_step": hx.numel() * hx.element_size() + ht.numel() * ht.element_size(),
+           "n_gpus": world,
+           "quantized_act_elems_per_step": {"resnet18": 1680896, "resnet20": 184320, "rfdn": 59093392}[a.qat_model] * B,
+           **res}
     if use_dist:   # replicas must hold identical parameters after the DDP steps
         import torch.distributed as dist
         chk = torch.stack([p.detach().double().sum() for p in q.model.parameters()]).sum().reshape(1)
@@ -495,13 +515,12 @@ def run_ours(a):
     if not a.no_resnet:
         rn = resnet18_leg(a, dev, world, rank, use_dist)
         if rank == 0:
-            out["resnet18_w4a4_qat" if (a.qat_model, a.qat_method, a.qat_bits) == ("resnet18", "STE", 4)
-                else f"{a.qat_model}_{a.qat_method.lower()}_w{a.qat_bits}a{a.qat_bits}_qat"] = rn
+            out[qat_key(a)] = rn
     if rank == 0:
         if not a.no_eager_ref:
             out["reference_eager_gpu"] = eager_reference_leg(a, dev)
             if not a.no_resnet and not use_dist:
-                key = "resnet18_w4a4_qat"
+                key = qat_key(a)
                 for cl in ((False, True) if a.channels_last else (False,)):
                     b = argparse.Namespace(**vars(a))
                     b.channels_last, b.graph = cl, False

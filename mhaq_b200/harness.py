@@ -133,16 +133,106 @@ class CifarResNet(nn.Module):
         return self.linear(out)
 
 
+class _Esa(nn.Module):
+    """Enhanced spatial attention of RFDN: 1x1 squeeze to n/4 channels, a strided 3x3 + 7x7/3
+    max-pool pyramid of three 3x3 convolutions, bilinear upsampling, sigmoid gate."""
+
+    def __init__(self, n):
+        super().__init__()
+        f = n // 4
+        self.conv1 = nn.Conv2d(n, f, 1)
+        self.conv_f = nn.Conv2d(f, f, 1)
+        self.conv_max = nn.Conv2d(f, f, 3, padding=1)
+        self.conv2 = nn.Conv2d(f, f, 3, stride=2, padding=0)
+        self.conv3 = nn.Conv2d(f, f, 3, padding=1)
+        self.conv3_ = nn.Conv2d(f, f, 3, padding=1)
+        self.conv4 = nn.Conv2d(f, n, 1)
+
+    def forward(self, x):
+        c1 = self.conv1(x)
+        v = F.max_pool2d(self.conv2(c1), kernel_size=7, stride=3)
+        v = F.relu(self.conv_max(v))
+        v = self.conv3_(F.relu(self.conv3(v)))
+        v = F.interpolate(v, (x.size(2), x.size(3)), mode="bilinear", align_corners=False)
+        return x * torch.sigmoid(self.conv4(v + self.conv_f(c1)))
+
+
+class _Rfdb(nn.Module):
+    """Residual feature distillation block: three (1x1 distil | 3x3 refine + skip) stages, a
+    final 3x3 distil, 1x1 fusion of the four distilled halves, ESA."""
+
+    def __init__(self, n):
+        super().__init__()
+        d = n // 2
+        self.c1_d, self.c1_r = nn.Conv2d(n, d, 1), nn.Conv2d(n, n, 3, padding=1)
+        self.c2_d, self.c2_r = nn.Conv2d(n, d, 1), nn.Conv2d(n, n, 3, padding=1)
+        self.c3_d, self.c3_r = nn.Conv2d(n, d, 1), nn.Conv2d(n, n, 3, padding=1)
+        self.c4 = nn.Conv2d(n, d, 3, padding=1)
+        self.c5 = nn.Conv2d(4 * d, n, 1)
+        self.esa = _Esa(n)
+
+    def forward(self, x):
+        act = lambda t: F.leaky_relu(t, 0.05)
+        d1, r = act(self.c1_d(x)), act(self.c1_r(x) + x)
+        d2, r2 = act(self.c2_d(r)), act(self.c2_r(r) + r)
+        d3, r3 = act(self.c3_d(r2)), act(self.c3_r(r2) + r2)
+        d4 = act(self.c4(r3))
+        return self.esa(self.c5(torch.cat([d1, d2, d3, d4], dim=1)))
+
+
+class Rfdn(nn.Module):
+    """RFDN super-resolution network (Liu et al., "Residual Feature Distillation Network for
+    Lightweight Image Super-Resolution", 2020): 50 features, 4 RFDBs, x4 pixel-shuffle — BASELINE
+    configs[4].  Module names (fea_conv, B1..B4, c, LR_conv, upsampler) follow the reference's
+    src/models/sr/rfdn/rfdn.py:11-42 so the YAML's excluded_layers
+    (`fea_conv`, `upsampler.0`) apply; 33 of its 3x3 convolutions get quantized, the 29 1x1
+    convolutions do not (reference quirk 2)."""
+
+    def __init__(self, in_nc=3, nf=50, num_modules=4, out_nc=3, scale=4):
+        super().__init__()
+        self.fea_conv = nn.Conv2d(in_nc, nf, 3, padding=1)
+        self.B1, self.B2, self.B3, self.B4 = (_Rfdb(nf) for _ in range(4))
+        self.c = nn.Sequential(nn.Conv2d(nf * num_modules, nf, 1), nn.LeakyReLU(0.05, inplace=True))
+        self.LR_conv = nn.Conv2d(nf, nf, 3, padding=1)
+        self.upsampler = nn.Sequential(nn.Conv2d(nf, out_nc * scale * scale, 3, padding=1),
+                                       nn.PixelShuffle(scale))
+
+    def forward(self, x):
+        fea = self.fea_conv(x)
+        b1 = self.B1(fea)
+        b2 = self.B2(b1)
+        b3 = self.B3(b2)
+        b4 = self.B4(b3)
+        out = self.LR_conv(self.c(torch.cat([b1, b2, b3, b4], dim=1))) + fea
+        return self.upsampler(out)
+
+
+class SRModule(LModule):
+    """LVisionSR's forward (vision_sr_module.py:49-53): the network sees 0..255 inputs."""
+
+    def forward(self, inputs):
+        return self.model(inputs * 255).div(255)
+
+    def training_step(self, batch, batch_idx):
+        inputs, target = batch
+        loss = self.criterion(self.forward(inputs), target)
+        self.log("loss", loss)
+        return loss
+
+
 def build_model(name: str, num_classes: Optional[int] = None) -> nn.Module:
     if name == "resnet18":
         import torchvision
         return torchvision.models.resnet18(num_classes=num_classes or 1000)
     if name == "resnet20":
         return CifarResNet(3, num_classes or 10)
+    if name == "rfdn":
+        return Rfdn(scale=4)
     raise ValueError(name)
 
 
-EXCLUDED = {"resnet18": ("conv1", "fc"), "resnet20": ("conv1", "linear")}
+EXCLUDED = {"resnet18": ("conv1", "fc"), "resnet20": ("conv1", "linear"),
+            "rfdn": ("fea_conv", "upsampler.0")}
 
 
 # ------------------------------------------------------------------ calibration
@@ -161,7 +251,7 @@ def calibrate(qmodel: LModule, batch, act_bits=10, weight_bits=10):
         handles = register_lightning_activation_forward_hook(model, MinMaxObserver())
         was_training = model.training
         model.eval()
-        model(batch)
+        qmodel(batch)          # through the module's own forward (LVisionSR denormalises)
         model.train(was_training)
         for h in handles:
             h.remove()
@@ -170,17 +260,20 @@ def calibrate(qmodel: LModule, batch, act_bits=10, weight_bits=10):
 
 # ------------------------------------------------------------------ build + fit
 def build_qat(model_name="resnet18", device="cuda", qnmethod="STE", act_bit=4, weight_bit=4,
-              distillation=True, num_classes=None, lr=3e-4, calib_batch=None):
+              distillation=True, num_classes=None, lr=3e-4, calib_batch=None, calib_bits=10):
     """FP model → LModule → Quantizer(config)().quantize(lm) → calibrated, on `device`."""
     from .quantization.quantizer import Quantizer
     model = build_model(model_name, num_classes).to(device)
-    lm = LModule(model, nn.CrossEntropyLoss(), torch.optim.RAdam, lr)
+    if model_name == "rfdn":      # config/gdnsq_config_rfdn_lsq_w2a2.yaml: L1, no teacher
+        lm = SRModule(model, nn.L1Loss(), torch.optim.RAdam, lr)
+    else:
+        lm = LModule(model, nn.CrossEntropyLoss(), torch.optim.RAdam, lr)
     cfg = make_config(act_bit=act_bit, weight_bit=weight_bit, qscheme=1, qnmethod=qnmethod,
                       excluded_layers=EXCLUDED[model_name], distillation=distillation)
     qmodel = Quantizer(cfg)().quantize(lm, in_place=True)
     qmodel.to(device)
     if calib_batch is not None:
-        calibrate(qmodel, calib_batch)
+        calibrate(qmodel, calib_batch, act_bits=calib_bits, weight_bits=calib_bits)
     return qmodel
 
 

@@ -117,3 +117,24 @@ def test_calibration_api_rebinds_parameters_like_the_reference():
     assert torch.allclose(act.log_act_s.detach(), log_s.reshape(1))
     assert torch.allclose(act.log_act_q.detach(), (log_s + 10).reshape(1))
     assert act.act_b.requires_grad and act.log_act_s.requires_grad
+
+
+def test_rfdn_surgery_matches_the_reference_inventory():
+    """BASELINE configs[4]: RFDN(scale=4) with excluded
+    ['fea_conv', 'upsampler.0'] -> 33 quantized 3x3 convolutions (358 236 weight elements),
+    the 29 1x1 convolutions untouched, every activation quantizer signed, L1 criterion wrapped
+    by PotentialLossNoPred (no teacher)."""
+    from mhaq_b200 import harness
+    from mhaq_b200.quantization.gdnsq.gdnsq_loss import PotentialLossNoPred
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+    q = harness.build_qat("rfdn", "cpu", qnmethod="LSQ", act_bit=2, weight_bit=2, distillation=False)
+    convs = [m for m in q.model.modules() if isinstance(m, NoisyConv2d)]
+    assert len(convs) == 33 and sum(c.weight.numel() for c in convs) == 358236
+    assert all(c.kernel_size == (3, 3) and c.Q.qnmethod == QNMethod.LSQ for c in convs)
+    plain = [m for m in q.model.modules() if type(m) is nn.Conv2d]
+    assert len(plain) == 29 + 2 and sum(m.kernel_size == (1, 1) for m in plain) == 29
+    assert type(q.model.fea_conv) is nn.Conv2d and type(q.model.upsampler[0]) is nn.Conv2d
+    acts = [m for m in q.model.modules() if isinstance(m, NoisyAct)]
+    assert len(acts) == 33 and all(a.signed for a in acts)
+    assert isinstance(q.wrapped_criterion, PotentialLossNoPred) and not hasattr(q, "tmodel")
+    assert sum(p.numel() for p in harness.Rfdn().parameters()) == 433448

@@ -25,17 +25,26 @@ def main():
     dev = torch.device("cuda", 0)
     torch.backends.cudnn.benchmark = True
     torch.set_float32_matmul_precision("high")
-    side, classes = (224, 1000) if a.model == "resnet18" else (32, 100)
-    x = torch.randn(a.batch, 3, side, side, device=dev)
-    t = torch.randint(0, classes, (a.batch,), device=dev)
-    q = harness.build_qat(a.model, dev, qnmethod=a.method, act_bit=a.bits, weight_bit=a.bits,
-                          distillation=True, num_classes=classes, calib_batch=x[:64])
+    if a.model == "rfdn":
+        x = torch.rand(a.batch, 3, 256, 256, device=dev)
+        t = torch.rand(a.batch, 3, 1024, 1024, device=dev)
+        q = harness.build_qat("rfdn", dev, qnmethod=a.method, act_bit=a.bits, weight_bit=a.bits,
+                              distillation=False, lr=5e-4, calib_batch=x[:4], calib_bits=a.bits)
+    else:
+        side, classes = (224, 1000) if a.model == "resnet18" else (32, 100)
+        x = torch.randn(a.batch, 3, side, side, device=dev)
+        t = torch.randint(0, classes, (a.batch,), device=dev)
+        q = harness.build_qat(a.model, dev, qnmethod=a.method, act_bit=a.bits, weight_bit=a.bits,
+                              distillation=True, num_classes=classes, calib_batch=x[:64])
     if a.channels_last:
         q.model.to(memory_format=torch.channels_last)
-        q.tmodel.to(memory_format=torch.channels_last)
+        if getattr(q, "tmodel", None) is not None:
+            q.tmodel.to(memory_format=torch.channels_last)
         x = x.contiguous(memory_format=torch.channels_last)
     opt = q.configure_optimizers()
-    q.train(); q.wrapped_criterion.train(); q.tmodel.eval()
+    q.train(); q.wrapped_criterion.train()
+    if getattr(q, "tmodel", None) is not None:
+        q.tmodel.eval()
 
     def step():
         loss = q.training_step((x, t), 0)
