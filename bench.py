@@ -222,7 +222,7 @@ class _EagerReferenceBackend:
             q.zero_point = weight.amin(tuple(range(1, weight.dim())), keepdim=True)
             wq = O.fake_quant(weight, q.scale, q.zero_point, -math.inf, math.inf,
                               method=q.qnmethod.name, noise=noise)
-            return wq, None, None
+            return wq, None, None, None
 
         def act_fake_quant(x, log_act_s, log_act_q, act_b, method="STE", noise=None, philox=None):
             return O.act_fake_quant(x, log_act_s, log_act_q, act_b, noise=noise, method=method)

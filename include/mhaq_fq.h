@@ -19,6 +19,9 @@
  *   mhaq_fq_rowstat_f32        weight.amin((1,2,3)) / amax of NoisyConv2d.forward
  *                              (layers/gdnsq_conv2d.py:80-84) and
  *                              ModelHelper.get_model_values (utils/model_helper.py:24-25)
+ *   mhaq_fq_wrow_fwd_f32 /     the whole per-channel weight path of NoisyConv2d / NoisyLinear.forward
+ *   mhaq_fq_wrow_bwd_f32       (gdnsq_conv2d.py:72-98) plus ModelHelper's log2(max-min+2^log_s)
+ *                              (utils/model_helper.py:24-25,44) and their autograd, one launch each
  *   mhaq_fq_minmax_finalize    q.aminmax() of NoisyAct.forward (layers/gdnsq_act.py:51-54)
  *                              and the eval-mode asserts (gdnsq.py:211-217)
  *   mhaq_fq_noise_f32          torch.randint_like(input, 2).sub_(0.5)  (gdnsq.py:54)
@@ -47,7 +50,7 @@
 extern "C" {
 #endif
 
-#define MHAQ_FQ_ABI_VERSION 3
+#define MHAQ_FQ_ABI_VERSION 4
 
 /* gradient estimators — numeric values follow the reference enum
  * QNMethod (src/quantization/gdnsq/gdnsq_utils.py:9-13). */
@@ -170,6 +173,32 @@ int mhaq_fq_rowstat_bwd_f32(const float *gx, const float *x, int64_t n_rows, int
                             const float *row_min, const float *n_at_min, const float *g_min,
                             const float *row_max, const float *n_at_max, const float *g_max,
                             float *out, void *stream);
+
+/* Row-resident fused WEIGHT quantizer (per-channel, channel = row, short rows: conv / linear
+ * weights).  One CTA per row, one launch:
+ *   row_min / row_max  = weight.amin / amax over the row  (gdnsq_conv2d.py:80-81,
+ *                        utils/model_helper.py:24-25)
+ *   wq        = fake_quant(w; s = exp2(log_scale[row]), zero_point = row_min)   (gdnsq_conv2d.py:72-98)
+ *   log_range = log2((row_max - row_min) + s)     (ModelHelper.get_model_values, model_helper.py:44)
+ * Any of wq / row_min / row_max / log_range may be NULL. */
+int mhaq_fq_wrow_fwd_f32(const float *w, float *wq, const float *log_scale,
+                         int64_t n_rows, int64_t n_inner,
+                         float *row_min, float *row_max, float *log_range, void *stream);
+
+/* Backward of mhaq_fq_wrow_fwd_f32 in one launch (methods STE / EWGS / LSQ; AEWGS needs an
+ * all-reduce between its two passes and stays on the streaming kernels):
+ *   g_w         = d/d w: the quantizer's input gradient plus the amin / amax backward (even split
+ *                 among ties) of everything that flowed into row_min / row_max — the zero-point
+ *                 gradient, g_row_min / g_row_max (NULL = none) and log_range's own dependence
+ *   g_log_scale = d/d log_scale[row], through the quantizer and through log_range
+ *   g_log_range : gradient w.r.t. the log_range output, or NULL
+ *   r / seed / offset / philox_dev : as mhaq_fq_bwd_f32 (same noise stream for the same shape). */
+int mhaq_fq_wrow_bwd_f32(const float *g_wq, const float *w, const float *log_scale,
+                         const float *row_min, const float *row_max,
+                         const float *g_log_range, const float *g_row_min, const float *g_row_max,
+                         int64_t n_rows, int64_t n_inner, int method,
+                         const float *r, uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                         float *g_w, float *g_log_scale, void *stream);
 
 /* Materialise the in-kernel noise stream: r[i] in {-0.5,+0.5}, identical to what
  * mhaq_fq_bwd_f32 draws for the same (seed, offset, philox_dev, shape). */

@@ -921,6 +921,8 @@ fq_rowstat_bwd_kernel(const float *__restrict__ gx, const float *__restrict__ x,
     }
 }
 
+#include "fq_wrow.cuh"
+
 // ===========================================================================
 // Host-side launch helpers
 // ===========================================================================
@@ -1000,6 +1002,20 @@ int launch_bwd_noise(bool explicit_r, bool vec, int grid, cudaStream_t st, const
                                                          r, seed, offset, philox_dev, stats, ws);
     return launch_bwd<METHOD, CLAMP, NOISE_PHILOX>(vec, grid, st, go, x, gx, prm, g, codegrad, r,
                                                    seed, offset, philox_dev, stats, ws);
+}
+
+template <int METHOD, int NOISE>
+int launch_wrow_bwd(bool vec, int grid, cudaStream_t st, const float *go, const float *w,
+                    const WRowArgs &a, const float *row_min, const float *row_max, const float *g_lr,
+                    const float *g_mn, const float *g_mx, const float *r, uint64_t seed,
+                    uint64_t offset, const uint64_t *philox_dev, float *gw, float *g_log_s) {
+    if (vec)
+        fq_wrow_bwd_kernel<METHOD, NOISE, true><<<grid, kThreads, 0, st>>>(
+            go, w, a, row_min, row_max, g_lr, g_mn, g_mx, r, seed, offset, philox_dev, gw, g_log_s);
+    else
+        fq_wrow_bwd_kernel<METHOD, NOISE, false><<<grid, kThreads, 0, st>>>(
+            go, w, a, row_min, row_max, g_lr, g_mn, g_mx, r, seed, offset, philox_dev, gw, g_log_s);
+    return last_error();
 }
 
 }  // namespace
@@ -1191,6 +1207,48 @@ int mhaq_fq_rowstat_bwd_f32(const float *gx, const float *x, int64_t n_rows, int
     fq_rowstat_bwd_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
         gx, x, n_rows, n_inner, row_min, n_at_min, g_min, row_max, n_at_max, g_max, out);
     return last_error();
+}
+
+int mhaq_fq_wrow_fwd_f32(const float *w, float *wq, const float *log_scale, int64_t n_rows,
+                         int64_t n_inner, float *row_min, float *row_max, float *log_range,
+                         void *stream) {
+    if (!w || !log_scale) return MHAQ_FQ_ENULL;
+    if (n_rows < 0 || n_inner <= 0) return MHAQ_FQ_EINVAL;
+    if (n_rows == 0) return 0;
+    const WRowArgs a = {log_scale, 1, n_rows, n_inner};
+    const bool vec = (n_inner % 4 == 0) && aligned16(w) && (!wq || aligned16(wq));
+    const int grid = grid_for(n_rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (vec)
+        fq_wrow_fwd_kernel<true><<<grid, kThreads, 0, st>>>(w, wq, a, row_min, row_max, log_range);
+    else
+        fq_wrow_fwd_kernel<false><<<grid, kThreads, 0, st>>>(w, wq, a, row_min, row_max, log_range);
+    return last_error();
+}
+
+int mhaq_fq_wrow_bwd_f32(const float *g_wq, const float *w, const float *log_scale,
+                         const float *row_min, const float *row_max, const float *g_log_range,
+                         const float *g_row_min, const float *g_row_max, int64_t n_rows,
+                         int64_t n_inner, int method, const float *r, uint64_t seed, uint64_t offset,
+                         const uint64_t *philox_dev, float *g_w, float *g_log_scale, void *stream) {
+    if (!g_wq || !w || !log_scale || !row_min || !row_max) return MHAQ_FQ_ENULL;
+    if (n_rows < 0 || n_inner <= 0) return MHAQ_FQ_EINVAL;
+    // AEWGS needs its statistics all-reduced between two passes: streaming kernels only
+    if (method != MHAQ_FQ_STE && method != MHAQ_FQ_EWGS && method != MHAQ_FQ_LSQ) return MHAQ_FQ_EINVAL;
+    if (n_rows == 0) return 0;
+    const WRowArgs a = {log_scale, 1, n_rows, n_inner};
+    const bool vec = (n_inner % 4 == 0) && aligned16(w) && aligned16(g_wq) && (!g_w || aligned16(g_w)) &&
+                     (!r || aligned16(r));
+    const int grid = grid_for(n_rows);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MHAQ_WROW(M, N)                                                                             \
+    launch_wrow_bwd<M, N>(vec, grid, st, g_wq, w, a, row_min, row_max, g_log_range, g_row_min,     \
+                          g_row_max, r, seed, offset, philox_dev, g_w, g_log_scale)
+    if (method == MHAQ_FQ_LSQ) return MHAQ_WROW(MHAQ_FQ_LSQ, NOISE_NONE);
+    if (method == MHAQ_FQ_STE)
+        return r ? MHAQ_WROW(MHAQ_FQ_STE, NOISE_EXPLICIT) : MHAQ_WROW(MHAQ_FQ_STE, NOISE_PHILOX);
+    return r ? MHAQ_WROW(MHAQ_FQ_EWGS, NOISE_EXPLICIT) : MHAQ_WROW(MHAQ_FQ_EWGS, NOISE_PHILOX);
+#undef MHAQ_WROW
 }
 
 int mhaq_fq_noise_f32(float *r, int64_t n_rows, int64_t n_inner, uint64_t seed, uint64_t offset,

@@ -3,7 +3,8 @@
 ``fake_quant_fwd_bwd_host`` streams a host-resident tensor through the GPU in row chunks:
 while chunk *i* is being quantized (one forward and one backward kernel), chunk *i+1* is on
 its way in over PCIe and the results of chunk *i-1* are on their way out, on three CUDA
-streams with double-buffered device staging.  PCIe is full duplex, so the end-to-end time
+streams with `stages`-deep device staging (3 by default: one chunk arriving, one computing or
+waiting, one leaving, so a late copy in one direction does not stall the other).  PCIe is full duplex, so the end-to-end time
 approaches max(bytes in, bytes out) / link bandwidth instead of their sum — this is the
 `e2e` leg of ``bench.py`` (inputs and outputs in pinned host memory, copies inside the timed
 region).
@@ -28,7 +29,7 @@ def _rows_view(t: torch.Tensor, rows: int) -> torch.Tensor:
 
 def fake_quant_fwd_bwd_host(x_host: torch.Tensor, go_host: torch.Tensor, scale, zero_point,
                             min_val=None, max_val=None, method="STE", y_host=None, gx_host=None,
-                            chunks: int = 8, device=None, philox=(0, 0)):
+                            chunks: int = 8, device=None, philox=(0, 0), stages: int = 3):
     """x_host, go_host: pinned fp32 host tensors of identical shape.  Parameters are CUDA
     tensors (per-tensor: numel 1; per-channel: one per row of dim 0).  Returns
     (y_host, gx_host, grads) with grads = dict(scale=..., zero_point=..., min_val=..., max_val=...)
@@ -63,11 +64,12 @@ def fake_quant_fwd_bwd_host(x_host: torch.Tensor, go_host: torch.Tensor, scale, 
     s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
     s_in.wait_stream(cur)
     max_elems = max((r1 - r0) * (c1 - c0) for r0, r1, c0, c1 in cuts)
+    stages = max(2, min(stages, len(cuts)))
     stage = [[torch.empty(max_elems, dtype=torch.float32, device=device) for _ in range(4)]
-             for _ in range(2)]                    # [x, go, y, gx] x double buffer
+             for _ in range(stages)]               # [x, go, y, gx] x `stages` buffers in flight
     ev_in = [torch.cuda.Event() for _ in cuts]
     ev_done = [torch.cuda.Event() for _ in cuts]
-    ev_out = [None, None]
+    ev_out = [None] * stages
     pshape = None
     acc = {k: None for k in ("scale", "zero_point", "min_val", "max_val")}
     prm = dict(scale=scale, zero_point=zero_point, min_val=min_val, max_val=max_val)
@@ -80,10 +82,10 @@ def fake_quant_fwd_bwd_host(x_host: torch.Tensor, go_host: torch.Tensor, scale, 
     def issue_in(i):
         r0, r1, c0, c1 = cuts[i]
         n = (r1 - r0) * (c1 - c0)
-        b = stage[i & 1]
+        b = stage[i % stages]
         with torch.cuda.stream(s_in):
-            if ev_out[i & 1] is not None:
-                s_in.wait_event(ev_out[i & 1])      # staging buffers free again
+            if ev_out[i % stages] is not None:
+                s_in.wait_event(ev_out[i % stages])      # staging buffers free again
             b[0][:n].view(r1 - r0, c1 - c0).copy_(x2[r0:r1, c0:c1], non_blocking=True)
             b[1][:n].view(r1 - r0, c1 - c0).copy_(g2[r0:r1, c0:c1], non_blocking=True)
             ev_in[i].record(s_in)
@@ -93,7 +95,7 @@ def fake_quant_fwd_bwd_host(x_host: torch.Tensor, go_host: torch.Tensor, scale, 
         if i + 1 < len(cuts):
             issue_in(i + 1)
         n = (r1 - r0) * (c1 - c0)
-        b = stage[i & 1]
+        b = stage[i % stages]
         shape = (r1 - r0, c1 - c0)
         cur.wait_event(ev_in[i])
         xd, gd = b[0][:n].view(shape), b[1][:n].view(shape)
@@ -133,7 +135,7 @@ def fake_quant_fwd_bwd_host(x_host: torch.Tensor, go_host: torch.Tensor, scale, 
             gx2[r0:r1, c0:c1].copy_(gxd, non_blocking=True)
             e = torch.cuda.Event()
             e.record(s_out)
-            ev_out[i & 1] = e
+            ev_out[i % stages] = e
         for t in (ws, out):
             t.record_stream(cur)
     cur.wait_stream(s_out)

@@ -335,19 +335,10 @@ def allreduce_packed_stats(stats: torch.Tensor) -> torch.Tensor:
     return stats
 
 
-def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_gx: bool,
-                   philox=None):
-    geo = L.geo
-    go = _like_layout(go, x)
-    gx = torch.empty_like(x) if need_gx else None
-    n_ch = geo.n_ch
-    if x.numel() == 0:
-        return gx, torch.zeros(4, n_ch, dtype=torch.float32, device=x.device)
-    out = torch.empty(4, n_ch, dtype=torch.float32, device=x.device)   # fully written by the kernel
-    if method == METHOD_IDS["AEWGS"] and geo.axis is None and x.dim() >= 2 and L.scale.dim() == 1:
-        return _backward_aewgs_dim0(go, x, L, code_grad, noise, need_gx, philox)
-    stats = aewgs_stats(go, x, L, code_grad) if method == METHOD_IDS["AEWGS"] else None
-    ws = _workspace(x, geo)
+def _noise_source(x, method: int, noise, philox):
+    """-> (explicit noise tensor in x's layout or None, seed, offset, device Philox state or None)
+    for one backward call: an explicit tensor (parity runs), a given (seed, offset), the
+    device-resident state (CUDA graphs) or a fresh draw from torch's CUDA generator."""
     seed = offset = 0
     pdev = None
     if noise is not None:
@@ -365,6 +356,23 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
                 _philox_call[x.device.index] = offset + 1
             else:
                 seed, offset = _next_philox(x.device)
+    return noise, seed, offset, pdev
+
+
+def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_gx: bool,
+                   philox=None):
+    geo = L.geo
+    go = _like_layout(go, x)
+    gx = torch.empty_like(x) if need_gx else None
+    n_ch = geo.n_ch
+    if x.numel() == 0:
+        return gx, torch.zeros(4, n_ch, dtype=torch.float32, device=x.device)
+    out = torch.empty(4, n_ch, dtype=torch.float32, device=x.device)   # fully written by the kernel
+    if method == METHOD_IDS["AEWGS"] and geo.axis is None and x.dim() >= 2 and L.scale.dim() == 1:
+        return _backward_aewgs_dim0(go, x, L, code_grad, noise, need_gx, philox)
+    stats = aewgs_stats(go, x, L, code_grad) if method == METHOD_IDS["AEWGS"] else None
+    ws = _workspace(x, geo)
+    noise, seed, offset, pdev = _noise_source(x, method, noise, philox)
     tk = _tickets(x, geo)
     check(lib.mhaq_fq_bwd_f32(_ptr(go), _ptr(x), _ptr(gx), *L.params(),
                               geo.n_rows, geo.n_inner, geo.n_ch, method, int(code_grad),
@@ -648,3 +656,71 @@ def weight_fake_quant_log(w, log_wght_s, method="STE", noise=None, philox=None):
     if log_wght_s.numel() != w.shape[0]:
         raise RuntimeError("weight_fake_quant_log expects one log-scale per output channel (dim 0)")
     return _WeightLogFakeQuantFn.apply(w, log_wght_s, _method_id(method), noise, philox)
+
+
+# ---------------------------------------------------------------------------------------------
+# Row-resident fused weight path (include/mhaq_fq.h: mhaq_fq_wrow_*): one launch forward, one
+# backward per layer, ModelHelper's log2(max - min + 2^log_s) included.
+# ---------------------------------------------------------------------------------------------
+WROW_MAX_INNER = 16384       # one CTA per row: conv / linear weight rows, not long tensors
+
+
+def weight_rows_fusable(w, log_wght_s, method) -> bool:
+    rows = w.shape[0] if w.dim() >= 1 else 0
+    return (rows > 0 and log_wght_s.numel() == rows and 0 < w.numel() // rows <= WROW_MAX_INNER
+            and _method_id(method) != METHOD_IDS["AEWGS"])
+
+
+class _WeightRowFn(torch.autograd.Function):
+    """(wq, row_min, row_max, log_range) = f(weight, log_wght_s), channel = dim 0:
+        row_min/max = weight.amin/amax over the row           (gdnsq_conv2d.py:80-81)
+        wq          = fake_quant(w; 2^log_wght_s, zp=row_min) (gdnsq_conv2d.py:72-98)
+        log_range   = log2(row_max - row_min + 2^log_wght_s)  (utils/model_helper.py:24-25,44)
+    with the reference's autograd for all of it, in one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, w, log_wght_s, method, noise, philox):
+        ctx.set_materialize_grads(False)
+        w = _dense(w, 0)
+        rows = w.shape[0]
+        inner = w.numel() // rows
+        ls = log_wght_s if log_wght_s.is_contiguous() else log_wght_s.contiguous()
+        wq = torch.empty_like(w)
+        o = torch.empty(3, rows, dtype=torch.float32, device=w.device)
+        check(lib.mhaq_fq_wrow_fwd_f32(_ptr(w), _ptr(wq), _ptr(ls), rows, inner, _ptr(o[0]), _ptr(o[1]),
+                                       _ptr(o[2]), _stream()), "mhaq_fq_wrow_fwd_f32")
+        mn, mx, lr = o[0], o[1], o[2]
+        ctx.save_for_backward(w, log_wght_s, mn, mx)
+        ctx.method, ctx.noise, ctx.philox = method, noise, philox
+        return wq, mn, mx, lr
+
+    @staticmethod
+    def backward(ctx, g_wq, g_mn, g_mx, g_lr):
+        w, log_wght_s, mn, mx = ctx.saved_tensors
+        rows = w.shape[0]
+        inner = w.numel() // rows
+        if g_wq is None:            # the quantized weight itself was not used downstream
+            g_wq = torch.zeros_like(w)
+        g_wq = _like_layout(g_wq, w)
+        noise, seed, offset, pdev = _noise_source(w, ctx.method, ctx.noise, ctx.philox)
+        c = lambda t: None if t is None else t.contiguous()
+        g_mn, g_mx, g_lr = c(g_mn), c(g_mx), c(g_lr)
+        ls = log_wght_s if log_wght_s.is_contiguous() else log_wght_s.contiguous()
+        gw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
+        gls = torch.empty(rows, dtype=torch.float32, device=w.device)
+        check(lib.mhaq_fq_wrow_bwd_f32(_ptr(g_wq), _ptr(w), _ptr(ls), _ptr(mn), _ptr(mx), _ptr(g_lr),
+                                       _ptr(g_mn), _ptr(g_mx), rows, inner, ctx.method, _ptr(noise),
+                                       seed, offset, _ptr(pdev), _ptr(gw), _ptr(gls), _stream()),
+              "mhaq_fq_wrow_bwd_f32")
+        return (gw, gls.reshape(log_wght_s.shape) if ctx.needs_input_grad[1] else None,
+                None, None, None)
+
+
+def weight_fake_quant_rows(w, log_wght_s, method="STE", noise=None, philox=None):
+    """(wq, row_min, row_max, log_range) for a per-channel weight with short rows; see
+    _WeightRowFn.  Check `weight_rows_fusable` first."""
+    _require_cuda(w)
+    if not weight_rows_fusable(w, log_wght_s, method):
+        raise RuntimeError("weight_fake_quant_rows: needs one log-scale per row of dim 0, rows of at "
+                           f"most {WROW_MAX_INNER} elements and a method other than AEWGS")
+    return _WeightRowFn.apply(w, log_wght_s, _method_id(method), noise, philox)

@@ -172,17 +172,25 @@ class Quantizer:
         """Per-channel weight path with the row-minimum zero point computed in the same pass
         (sets self.zero_point like NoisyConv2d.forward does, gdnsq_conv2d.py:80-84).
         With `log_scale` (= log_wght_s) the kernels take the scale in the log domain and
-        return d/d log_wght_s directly; self.scale is then materialised lazily.
-        Returns (weight_q, row_min, row_max)."""
+        return d/d log_wght_s directly; self.scale is then materialised lazily.  Short rows
+        (conv / linear weights) and a method other than AEWGS take the row-resident fused
+        kernels: one launch each way, which also yield ModelHelper's
+        log2(row_max - row_min + 2^log_wght_s) (utils/model_helper.py:24-25,44).
+        Returns (weight_q, row_min, row_max, log_range or None)."""
         pshape = (weight.shape[0],) + (1,) * (weight.dim() - 1)
+        lr = None
         if log_scale is not None:
-            wq, mn, mx = ops.weight_fake_quant_log(weight, log_scale, method=self._method(), noise=noise)
+            if ops.weight_rows_fusable(weight, log_scale, self._method()):
+                wq, mn, mx, lr = ops.weight_fake_quant_rows(weight, log_scale, method=self._method(),
+                                                            noise=noise)
+            else:
+                wq, mn, mx = ops.weight_fake_quant_log(weight, log_scale, method=self._method(), noise=noise)
             zp = mn.view(pshape)
             self.defer(lambda: (torch.exp2(log_scale).reshape(pshape), zp, self._min_val, self._max_val))
         else:
             wq, mn, mx = ops.weight_fake_quant(weight, self.scale, method=self._method(), noise=noise)
             self.zero_point = mn.view(pshape)
-        return wq, mn, mx
+        return wq, mn, mx, lr
 
     def fake_quant_eval(self, value):
         """No-grad fused forward that also yields (min code, max code, #non-finite) — the

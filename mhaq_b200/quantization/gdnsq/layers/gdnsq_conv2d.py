@@ -44,25 +44,30 @@ class NoisyConv2d(nn.Conv2d):
 
     def quantized_weight(self):
         """(weight_q, bias_q) — computed once per parameter version (see _wcache)."""
-        w, b, _, _ = self._quantize()
-        return w, b
+        out = self._quantize()
+        return out[0], out[1]
 
     def row_range(self):
         """(row_min, row_max) of the weight, differentiable, from the same pass that produced
         the quantized weight (consumed by ModelHelper.get_model_values); None per-tensor."""
-        _, _, mn, mx = self._quantize()
-        return (mn, mx) if mn is not None else None
+        out = self._quantize()
+        return (out[2], out[3]) if out[2] is not None else None
+
+    def log_w_range(self):
+        """log2(row_max - row_min + 2^log_wght_s) per output channel, differentiable, when the
+        fused row kernels produced it in this step's quantization pass (else None)."""
+        return self._quantize()[4]
 
     def _quantize(self):
         key, hit = self._wq_cache.lookup((self.weight, self.log_wght_s, self.bias),
                                          torch.is_grad_enabled(), self.training)
         if hit is not None:
             return hit
-        mx = None
+        mx = lr = None
         if self.qscheme == QScheme.PER_CHANNEL and self.positive_scale_ok():
             # fused: row min (zero point) + row max in one pass, quantization in the next, the
             # scale taken in the log domain (no exp2 / Exp2Backward launches)
-            weight, mn_flat, mx = self.Q.fake_quant_weight(self.weight, log_scale=self.log_wght_s)
+            weight, mn_flat, mx, lr = self.Q.fake_quant_weight(self.weight, log_scale=self.log_wght_s)
             s = mn = None
         else:
             s = torch.exp2(self.log_wght_s)
@@ -83,7 +88,7 @@ class NoisyConv2d(nn.Conv2d):
             bias = self.Q_b.fake_quant(self.bias)
         else:
             bias = self.bias
-        out = (weight, bias, mn_flat, mx)
+        out = (weight, bias, mn_flat, mx, lr)
         # a quantized bias (tiny) is recomputed per call so that one cache entry never pins
         # two autograd graphs
         if not self.quant_bias:

@@ -40,8 +40,12 @@ class NoisyLinear(nn.Linear):
 
     def row_range(self):
         """(row_min, row_max), differentiable, from the quantization pass; None per-tensor."""
-        _, mn, mx = self._quantize()
-        return (mn, mx) if mn is not None else None
+        out = self._quantize()
+        return (out[1], out[2]) if out[1] is not None else None
+
+    def log_w_range(self):
+        """log2(row_max - row_min + 2^log_wght_s) from the fused row kernels, or None."""
+        return self._quantize()[3]
 
     def _quantize(self):
         key, hit = self._wq_cache.lookup((self.weight, self.log_wght_s), torch.is_grad_enabled(),
@@ -54,11 +58,11 @@ class NoisyLinear(nn.Linear):
             else:
                 self.Q.scale = torch.exp2(self.log_wght_s).reshape(self.out_features, 1)
                 self.Q.zero_point = self.weight.amin(1, keepdim=True)
-                out = (self.Q.fake_quant(self.weight), None, None)
+                out = (self.Q.fake_quant(self.weight), None, None, None)
         else:
             self.Q.scale = torch.exp2(self.log_wght_s)
             self.Q.zero_point = self.weight.amin()
-            out = (self.Q.fake_quant(self.weight), None, None)
+            out = (self.Q.fake_quant(self.weight), None, None, None)
         self._wq_cache.store(key, out)
         return out
 

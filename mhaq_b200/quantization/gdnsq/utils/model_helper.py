@@ -22,10 +22,16 @@ class ModelHelper:
                 if qscheme == QScheme.PER_CHANNEL:
                     dims = tuple(range(1, m.weight.dim()))
                     log_wght_s.append(m.log_wght_s.ravel())
-                    # the layer already reduced the weight rows in this step's forward (fused
-                    # row-stat kernel); reuse its differentiable (min, max) instead of two more
+                    # the layer already reduced the weight rows in this step's forward: the
+                    # fused row kernels hand back log2(max - min + 2^log_wght_s) itself, the
+                    # streaming path its differentiable (min, max) — either way no further
                     # passes over the weight
-                    rr = m.row_range() if hasattr(m, "row_range") and m.weight.is_cuda else None
+                    on_gpu = m.weight.is_cuda
+                    lr = m.log_w_range() if on_gpu and hasattr(m, "log_w_range") else None
+                    if lr is not None:
+                        log_w_n_b.append(lr)
+                        continue
+                    rr = m.row_range() if on_gpu and hasattr(m, "row_range") else None
                     mn, mx = rr if rr is not None else (m.weight.amin(dims), m.weight.amax(dims))
                 else:
                     log_wght_s.append(m.log_wght_s)

@@ -385,6 +385,7 @@ def test_autograd_functions_do_not_leak_their_graph():
     la, lq, ab = (torch.tensor([v], device="cuda", requires_grad=True) for v in (-2.0, 2.0, -2.0))
     for run_backward in (True, False):
         outs = list(ops.weight_fake_quant_log(w, ls, method="LSQ"))
+        outs += list(ops.weight_fake_quant_rows(w, ls, method="LSQ"))
         outs += list(ops.weight_fake_quant(w, torch.exp2(ls), method="LSQ"))
         outs.append(ops.act_fake_quant(x, la, lq, ab, method="LSQ"))
         outs.append(ops.fake_quant(x, torch.exp2(la), ab, ab, ab + 3.0, method="LSQ"))

@@ -550,3 +550,144 @@ def test_channels_last_weight_equals_row_major(fq, shape, method):
     else:
         H.assert_close_rel(res[1][1], res[0][1], REL, "g_weight", abs_floor=2e-5)
     H.assert_close_rel(res[1][2], res[0][2], REL, "g_log_wght_s", abs_floor=2e-5)
+
+
+# ---------------------------------------------------------------------------
+# row-resident fused weight kernels (mhaq_fq_wrow_*): one launch each way
+# ---------------------------------------------------------------------------
+WROW_SHAPES = [(64, 64, 3, 3), (32, 50, 3, 3), (16, 512, 3, 3), (12, 12, 3, 3), (24, 40), (7, 1, 3, 3),
+               (3, 16384), (5, 4099)]
+
+
+@pytest.mark.parametrize("shape", WROW_SHAPES)
+@pytest.mark.parametrize("method", ["STE", "LSQ", "EWGS"])
+def test_fused_weight_rows_match_oracle_and_streaming_path(fq, shape, method):
+    """(wq, row_min, row_max, log2(max-min+2^log_s)) and every gradient of the fused per-row
+    kernels against (a) the oracle's op-for-op restatement of NoisyConv2d.forward's weight lines
+    plus ModelHelper's expression under torch autograd on the CPU and (b) the streaming kernels."""
+    ops = fq.ops
+    g = torch.Generator().manual_seed(zlib.crc32(repr((shape, method)).encode()))
+    w = torch.randn(shape, generator=g)
+    w[0].view(-1)[:3] = w[0].min()                  # ties at the row minimum ...
+    w[-1].view(-1)[-2:] = w[-1].max()               # ... and at the row maximum
+    go = torch.randn(shape, generator=g)
+    gl = torch.randn(shape[0], generator=g)
+    r = torch.randint(0, 2, shape, generator=g).float() - 0.5
+    pshape = (shape[0],) + (1,) * (len(shape) - 1)
+    log_s = torch.full(pshape, -3.0) + 0.25 * torch.rand(pshape, generator=g)
+    noise = None if method == "LSQ" else r
+    dims = tuple(range(1, len(shape)))
+
+    def reference(dev):
+        wr = w.to(dev).clone().requires_grad_(True)
+        ls = log_s.to(dev).clone().requires_grad_(True)
+        wq = O.weight_fake_quant(wr, ls, True, method, noise=None if noise is None else noise.to(dev))
+        lr = torch.log2(wr.amax(dims) - wr.amin(dims) + torch.exp2(ls.ravel()))
+        ((wq * go.to(dev)).sum() + (lr * gl.to(dev)).sum()).backward()
+        return wq.detach(), lr.detach(), wr.grad, ls.grad
+
+    # exp2 is evaluated inside the kernels (CUDA exp2f == torch's CUDA exp2 kernel, while the
+    # CPU's vectorised exp2 may differ in the last bit): the op-for-op oracle therefore runs on
+    # the device for fractional log-scales ...
+    wq_o, lr_o, gw_o, gs_o = reference("cuda")
+    assert ops.weight_rows_fusable(w.cuda(), log_s.cuda(), method)
+    # The weight gradient is the per-element quantizer gradient (deterministic: bit-exact) plus,
+    # on the row's min / max elements only, the amin / amax backward of the zero-point gradient.
+    # That term is sum(go) - sum(g_u) accumulated in fp32 by the reference — rounding noise that
+    # grows with the row length — while the kernels sum the per-element differences in fp64.
+    n_inner = w[0].numel()
+    flat = w.reshape(shape[0], -1)
+    ties = ((flat == flat.amin(1, keepdim=True)) | (flat == flat.amax(1, keepdim=True))).reshape(shape)
+    tie_floor = max(2e-5, 1.5e-6 * math.sqrt(n_inner))
+
+    # d/d log_wght_s: the reference's fp32 value is itself only good to ~1e-4 on long rows (two
+    # big fp32 sums that nearly cancel, see the module docstring); the streaming kernels are
+    # pinned against the exact fp64 value elsewhere in this file, so long rows are held to the
+    # reference loosely here and to the streaming path tightly below.
+    gs_rel = REL if n_inner <= 1024 else 1e-3
+
+    def check_gw(ours, ref, what):
+        ours, ref = ours.detach().cpu(), ref.detach().cpu()
+        H.assert_bit_exact(ours[~ties], ref[~ties], what + " (off the row extrema)")
+        H.assert_close_rel(ours[ties], ref[ties], REL, what + " (row extrema)", abs_floor=tie_floor)
+
+    wr = w.cuda().requires_grad_(True)
+    ls = log_s.cuda().requires_grad_(True)
+    wq, mn, mx, lr = ops.weight_fake_quant_rows(wr, ls, method=method, noise=None if noise is None else noise.cuda())
+    ((wq * go.cuda()).sum() + (lr * gl.cuda()).sum()).backward()
+    H.assert_bit_exact(wq, wq_o, "wq")
+    H.assert_bit_exact(mn, w.amin(dims), "row_min")
+    H.assert_bit_exact(mx, w.amax(dims), "row_max")
+    H.assert_close_rel(lr, lr_o, 1e-6, "log_range", abs_floor=1e-6)
+    check_gw(wr.grad, gw_o, "g_weight")
+    H.assert_close_rel(ls.grad, gs_o, gs_rel, "g_log_wght_s", abs_floor=5e-5)
+    # ... and on the CPU for integer log-scales, where exp2 is exact everywhere
+    log_s_frac, log_s = log_s, log_s.round()
+    wq_c, lr_c, gw_c, gs_c = reference("cpu")
+    wr1 = w.cuda().requires_grad_(True)
+    ls1 = log_s.cuda().requires_grad_(True)
+    wq1, _, _, lr1 = ops.weight_fake_quant_rows(wr1, ls1, method=method, noise=None if noise is None else noise.cuda())
+    ((wq1 * go.cuda()).sum() + (lr1 * gl.cuda()).sum()).backward()
+    H.assert_bit_exact(wq1, wq_c, "wq (CPU oracle)")
+    H.assert_close_rel(lr1, lr_c, 1e-6, "log_range (CPU oracle)", abs_floor=1e-6)
+    check_gw(wr1.grad, gw_c, "g_weight (CPU oracle)")
+    H.assert_close_rel(ls1.grad, gs_c, gs_rel, "g_log_wght_s (CPU oracle)", abs_floor=5e-5)
+    log_s = log_s_frac
+    # the streaming path + torch autograd for the range term, on the same device
+    wr2 = w.cuda().requires_grad_(True)
+    ls2 = log_s.cuda().requires_grad_(True)
+    wq2, mn2, mx2 = ops.weight_fake_quant_log(wr2, ls2, method=method, noise=None if noise is None else noise.cuda())
+    lr2 = torch.log2(mx2 - mn2 + torch.exp2(ls2.ravel()))
+    ((wq2 * go.cuda()).sum() + (lr2 * gl.cuda()).sum()).backward()
+    H.assert_bit_exact(wq, wq2, "wq vs streaming")
+    H.assert_bit_exact(lr, lr2, "log_range vs torch.log2 on the device")
+    H.assert_close_rel(wr.grad, wr2.grad, REL, "g_weight vs streaming", abs_floor=2e-6)
+    H.assert_close_rel(ls.grad, ls2.grad, REL, "g_log_wght_s vs streaming", abs_floor=2e-6)
+
+
+@pytest.mark.parametrize("shape", [(32, 50, 3, 3), (16, 512, 3, 3), (3, 16384)])
+def test_fused_weight_rows_philox_stream_is_the_streaming_kernels_stream(fq, shape):
+    """Same (seed, offset, row, position) -> same noise bit as mhaq_fq_bwd_f32 / mhaq_fq_noise_f32."""
+    ops = fq.ops
+    g = torch.Generator().manual_seed(11)
+    w = torch.randn(shape, generator=g).cuda()
+    go = torch.randn(shape, generator=g).cuda()
+    log_s = torch.full((shape[0],) + (1,) * (len(shape) - 1), -3.0).cuda()
+    r = ops.philox_noise(w, log_s, seed=77, offset=5)
+    res = []
+    for kw in (dict(philox=(77, 5)), dict(noise=r)):
+        ls = log_s.clone().requires_grad_(True)
+        wr = w.clone().requires_grad_(True)
+        wq, _, _, _ = ops.weight_fake_quant_rows(wr, ls, method="STE", **kw)
+        wq.backward(go)
+        res.append((wr.grad, ls.grad))
+    H.assert_bit_exact(res[0][0], res[1][0], "g_weight")
+    H.assert_bit_exact(res[0][1], res[1][1], "g_log_wght_s")
+
+
+def test_fused_weight_rows_channels_last_and_unused_outputs(fq):
+    ops = fq.ops
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(16, 8, 3, 3, generator=g).cuda()
+    log_s = torch.full((16, 1, 1, 1), -3.0).cuda()
+    outs = []
+    for conv in (lambda t: t, _cl):
+        wr = conv(w).clone(memory_format=torch.preserve_format).requires_grad_(True)
+        ls = log_s.clone().requires_grad_(True)
+        wq, mn, mx, lr = ops.weight_fake_quant_rows(wr, ls, method="LSQ")
+        assert wq.stride() == wr.stride()
+        lr.sum().backward()                       # only the range term is used (wq's grad is None)
+        assert wr.grad.stride() == wr.stride()
+        outs.append((wq.detach(), wr.grad, ls.grad))
+    H.assert_bit_exact(outs[1][0], outs[0][0], "wq")
+    H.assert_bit_exact(outs[1][1], outs[0][1], "g_weight")
+    H.assert_bit_exact(outs[1][2], outs[0][2], "g_log_wght_s")
+    # against torch autograd of the range term alone
+    wr = w.clone().requires_grad_(True)
+    ls = log_s.clone().requires_grad_(True)
+    torch.log2(wr.amax((1, 2, 3)) - wr.amin((1, 2, 3)) + torch.exp2(ls.ravel())).sum().backward()
+    H.assert_close_rel(outs[0][1], wr.grad, REL, "g_weight (range only)", abs_floor=1e-6)
+    H.assert_close_rel(outs[0][2], ls.grad, REL, "g_log_wght_s (range only)", abs_floor=1e-6)
+    assert not ops.weight_rows_fusable(w, log_s, "AEWGS")
+    with pytest.raises(RuntimeError):
+        ops.weight_fake_quant_rows(torch.randn(2, 20000, device="cuda"), log_s[:2], method="STE")
