@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--method", default="STE")
     ap.add_argument("--bits", type=int, default=4)
     ap.add_argument("--top", type=int, default=25)
+    ap.add_argument("--by-count", action="store_true", help="sort by launches per step instead of time")
     a = ap.parse_args()
     from mhaq_b200 import harness
     dev = torch.device("cuda", 0)
@@ -71,7 +72,7 @@ def main():
         dt = getattr(ev, "device_time_total", 0.0) or 0.0
         if dt > 0:
             rows.append((dt / 2e3, ev.count // 2, ev.key))
-    rows.sort(reverse=True)
+    rows.sort(reverse=True, key=(lambda r: (r[1], r[0])) if a.by_count else None)
     tot = sum(r[0] for r in rows)
     print(f"# GPU kernel time {tot:.2f} ms/step over {sum(r[1] for r in rows)} launches/step")
     for ms, n, k in rows[: a.top]:
