@@ -318,8 +318,26 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
 
     graphed = None
     if a.graph:
-        del opt
-        graphed = harness.GraphedTrainStep(q, (x, t), seed=1234 + rank)
+        # capture; if it fails on ANY rank every rank falls back to eager launches (the bench
+        # line must not depend on a capture succeeding) and says so
+        note = None
+        try:
+            graphed = harness.GraphedTrainStep(q, (x, t), seed=1234 + rank)
+        except Exception as exc:
+            note = f"{type(exc).__name__}: {str(exc)[:160]}"
+        ok = torch.tensor([0 if graphed is None else 1], device=dev)
+        if use_dist:
+            import torch.distributed as dist
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if graphed is not None:
+                graphed.close()
+            graphed = None
+            from mhaq_b200 import ops as _ops
+            _ops.set_device_philox_state(None)
+            torch.cuda.synchronize()
+            opt = q.configure_optimizers()
+            res["graph_capture_failed"] = note or "capture failed on another rank"
     step = graphed if graphed is not None else eager_step
 
     # end to end: every step's batch comes from pinned host memory (H2D inside the timed region,
@@ -483,37 +501,49 @@ def run_ours(a):
 
     # ---- end to end through the public API with HOST buffers -------------------------
     if not a.no_e2e:
-        from mhaq_b200.host import fake_quant_fwd_bwd_host
-        hx = torch.empty(x.shape, dtype=torch.float32).pin_memory()
-        hg = torch.empty(x.shape, dtype=torch.float32).pin_memory()
-        hx.copy_(x.detach()); hg.copy_(go)
-        hy = torch.empty(x.shape, dtype=torch.float32).pin_memory()
-        hgx = torch.empty(x.shape, dtype=torch.float32).pin_memory()
-        hgs = torch.empty(scale.shape, dtype=torch.float32).pin_memory()
-        del x, go                       # the e2e leg owns its (staged) device memory
-        torch.cuda.empty_cache()
+        try:
+            from mhaq_b200.host import fake_quant_fwd_bwd_host
+            hx = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+            hg = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+            hx.copy_(x.detach()); hg.copy_(go)
+            hy = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+            hgx = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+            hgs = torch.empty(scale.shape, dtype=torch.float32).pin_memory()
+            del x, go                       # the e2e leg owns its (staged) device memory
+            torch.cuda.empty_cache()
 
-        def e2e_step():
-            _, _, grads = fake_quant_fwd_bwd_host(hx, hg, scale, zp, lo, hi, method=a.method,
-                                                  y_host=hy, gx_host=hgx, chunks=16)
-            hgs.copy_(grads["scale"], non_blocking=True)
+            def e2e_step():
+                _, _, grads = fake_quant_fwd_bwd_host(hx, hg, scale, zp, lo, hi, method=a.method,
+                                                      y_host=hy, gx_host=hgx, chunks=16)
+                hgs.copy_(grads["scale"], non_blocking=True)
 
-        ke = max(3, min(a.steps, 5))
-        for _ in range(2):
-            e2e_step()
-        ms_e = time_region(e2e_step, ke, use_dist) / ke
-        if rank == 0:
-            out["e2e"] = {"value": round(world * 20 * n / (ms_e * 1e-3) / 1e9, 2), "unit": "GB/s",
-                          "h2d_bytes_per_step": 2 * 4 * n, "d2h_bytes_per_step": 2 * 4 * n + 4 * scale.numel(),
-                          "ms_per_step": round(ms_e, 3), "steps": ke,
-                          "api": "mhaq_b200.host.fake_quant_fwd_bwd_host: pinned host x/go in, y/gx/g_scale out, "
-                                 "16 row chunks pipelined over full-duplex PCIe (copies inside the timed region)"}
-        del hx, hg, hy, hgx
+            ke = max(3, min(a.steps, 5))
+            for _ in range(2):
+                e2e_step()
+            ms_e = time_region(e2e_step, ke, use_dist) / ke
+            if rank == 0:
+                out["e2e"] = {"value": round(world * 20 * n / (ms_e * 1e-3) / 1e9, 2), "unit": "GB/s",
+                              "h2d_bytes_per_step": 2 * 4 * n, "d2h_bytes_per_step": 2 * 4 * n + 4 * scale.numel(),
+                              "ms_per_step": round(ms_e, 3), "steps": ke,
+                              "api": "mhaq_b200.host.fake_quant_fwd_bwd_host: pinned host x/go in, y/gx/g_scale out, "
+                                     "16 row chunks pipelined over full-duplex PCIe (copies inside the timed region)"}
+            del hx, hg, hy, hgx
+        except Exception as exc:       # e.g. the box refuses 4 GiB of pinned host memory
+            if use_dist:
+                raise
+            if rank == 0:
+                out["e2e"] = {"value": None, "unit": "GB/s", "error": f"{type(exc).__name__}: {str(exc)[:200]}"}
 
     x = go = None
     torch.cuda.empty_cache()
     if not a.no_resnet:
-        rn = resnet18_leg(a, dev, world, rank, use_dist)
+        try:
+            rn = resnet18_leg(a, dev, world, rank, use_dist)
+        except Exception as exc:       # the QAT leg must never take the headline line down with it
+            if use_dist:
+                raise
+            rn = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+            torch.cuda.empty_cache()
         if rank == 0:
             out[qat_key(a)] = rn
     if rank == 0:
@@ -524,8 +554,14 @@ def run_ours(a):
                 for cl in ((False, True) if a.channels_last else (False,)):
                     b = argparse.Namespace(**vars(a))
                     b.channels_last, b.graph = cl, False
-                    with _EagerReferenceBackend():
-                        rr = resnet18_leg(b, dev, 1, 0, False, profile_share=False)
+                    try:
+                        with _EagerReferenceBackend():
+                            rr = resnet18_leg(b, dev, 1, 0, False, profile_share=False)
+                    except Exception as exc:
+                        out["reference_eager_gpu"][key + ("_channels_last" if cl else "")] = {
+                            "error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+                        torch.cuda.empty_cache()
+                        continue
                     out["reference_eager_gpu"][key + ("_channels_last" if cl else "")] = {
                         "img_per_s": rr["img_per_s"], "ms_per_step": rr["ms_per_step"],
                         "what": "same QAT step with every fake-quant routed through the reference's eager "
