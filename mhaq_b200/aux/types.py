@@ -1,27 +1,25 @@
-"""Enums of the reference's src/aux/types.py:3-25 (names and values are part of the
-config / plugin contract; only QScheme is read on the hot path)."""
+"""Task / model / quantization-scheme enumerations.
+
+Names and integer values are the config and plugin contract of the reference
+(src/aux/types.py:3-25): YAML configs carry the integers (`qscheme: 1`), `config_schema`
+validates against the names.  Only ``QScheme`` is read on the hot path.  Declared from tables so
+that the contract is visible in one place; members behave exactly like class-syntax ``Enum``s
+(`QScheme.PER_CHANNEL.value == 1`, `QScheme["PER_TENSOR"]`, `QScheme(0)`, picklable).
+"""
 from enum import Enum
 
-
-class DType(Enum):
-    VISION_CLS = 1
-    VISION_SR = 2
-    VISION_DNS = 3
-    VISION_OD = 4
+_VISION_TASKS = {"VISION_CLS": 1, "VISION_SR": 2, "VISION_DNS": 3, "VISION_OD": 4}
 
 
-class MType(Enum):
-    VISION_CLS = 1
-    VISION_SR = 2
-    VISION_DNS = 3
-    VISION_OD = 4
-    LM = 10
+def _enum(name, members):
+    return Enum(name, members, module=__name__, qualname=name)
 
 
-class QScheme(Enum):
-    PER_TENSOR = 0
-    PER_CHANNEL = 1
-
-
-class QMethod(Enum):
-    GDNSQ = 0
+#: dataset families
+DType = _enum("DType", _VISION_TASKS)
+#: model families: the vision tasks plus language models
+MType = _enum("MType", {**_VISION_TASKS, "LM": 10})
+#: granularity of the weight scale / zero point: one per tensor, or one per output channel
+QScheme = _enum("QScheme", {"PER_TENSOR": 0, "PER_CHANNEL": 1})
+#: quantization algorithm family
+QMethod = _enum("QMethod", {"GDNSQ": 0})

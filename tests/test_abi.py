@@ -79,3 +79,17 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_estimator_ids_agree_between_header_enum_and_ops():
+    """QNMethod values (the reference's, gdnsq_utils.py:9-13) are the ABI's `method` ids."""
+    import re
+    from mhaq_b200 import ops
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod, QMode
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                            "include", "mhaq_fq.h")).read()
+    ids = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define MHAQ_FQ_(STE|EWGS|AEWGS|LSQ) (\d+)", hdr)}
+    assert ids == {"STE": 0, "EWGS": 1, "AEWGS": 2, "LSQ": 3}
+    assert {m.name: m.value for m in QNMethod} == ids == ops.METHOD_IDS
+    assert [m.name for m in QMode] == ["NOISE_VAL", "ROUND_VAL", "SOURCE_VAL", "FLOAT_TRAIN_VAL"]
+    assert [m.value for m in QMode] == [1, 2, 3, 4]
