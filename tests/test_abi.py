@@ -93,3 +93,27 @@ def test_estimator_ids_agree_between_header_enum_and_ops():
     assert {m.name: m.value for m in QNMethod} == ids == ops.METHOD_IDS
     assert [m.name for m in QMode] == ["NOISE_VAL", "ROUND_VAL", "SOURCE_VAL", "FLOAT_TRAIN_VAL"]
     assert [m.value for m in QMode] == [1, 2, 3, 4]
+
+
+def test_header_is_plain_c():
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "mhaq_fq.h")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c", hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_plain_c_client_links_and_runs(tmp_path):
+    """A C99 program (no C++, no torch) compiled against include/mhaq_fq.h and linked with the
+    shared library runs the GPU-free entry points (version, geometry, argument validation)."""
+    import subprocess
+    from mhaq_b200 import _lib
+    exe = str(tmp_path / "abi_client")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", "abi_client.c"), "-o", exe,
+                        "-L", libdir, "-lmhaq_fq", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "abi_client OK" in r.stdout
