@@ -730,13 +730,50 @@ fq_aewgs_stats_kernel(const float *__restrict__ go, const float *__restrict__ x,
         const Task k = make_task(g, t);
         const QConst q = load_qconst(prm, k.ch);
         const float smul = codegrad ? 1.f : q.s;
+        const float rcp = __frcp_rn(q.s);
+        const bool fast_ok = VEC && scale_fast_ok(q.s);
         const float *xr = x + k.row_off;
         const float *gr = go + k.row_off;
         float a_num = 0.f, a_e2 = 0.f, a_e = 0.f;
         for (int64_t sub = k.q0; sub < k.q1; ++sub) {
             const int64_t base = sub * kSubElems + tid * 4;
             const bool full = (sub + 1) * kSubElems <= g.n_inner;
+            if (fast_ok && full) {
+                // ---- fast path: full aligned sub-tile, division by the hoisted reciprocal
+                // (bit-identical to IEEE division, see div_exact; |x| > 2^80 -> general path) ----
 #pragma unroll
+                for (int b = 0; b < kSubIters / kU; ++b) {
+                    float4 xv[kU], gv[kU];
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const int64_t p = base + (b * kU + u) * kIterElems;
+                        xv[u] = ld_stream4(xr + p);
+                        gv[u] = ld_stream4(gr + p);
+                    }
+                    float mx = 0.f;
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) mx = absmax4(mx, xv[u]);
+                    const bool huge = mx > kXHi;
+#pragma unroll
+                    for (int u = 0; u < kU; ++u) {
+                        const float xe[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                        const float ge[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float uu = f_sub(f_clamp(xe[i], q.lo, q.hi), q.zp);
+                            const float v = huge ? f_div(uu, q.s) : div_exact(uu, q.s, rcp);
+                            const float e = f_sub(rintf(v), v);
+                            const float gg = f_mul(ge[i], smul);
+                            const float sg = (gg > 0.f) ? 1.f : ((gg < 0.f) ? -1.f : 0.f);
+                            a_num += f_mul(sg, e);
+                            a_e2 += f_mul(e, e);
+                            a_e += e;
+                        }
+                    }
+                }
+                continue;
+            }
+#pragma unroll 1
             for (int b = 0; b < kSubIters / kU; ++b) {
                 float4 xv[kU], gv[kU];
                 int nv[kU];
