@@ -39,6 +39,7 @@ fq_wrow_fwd_kernel(const float *__restrict__ w, float *__restrict__ wq, WRowArgs
         const float *xr = w + row * a.n_inner;
         // ---- pass 1: row minimum / maximum (same merge as fq_rowstat_kernel) ----
         RowStat st = {INFINITY, -INFINITY, 0.f, 0.f};
+#pragma unroll 4
         for (int64_t p = (int64_t)tid * 4; p < a.n_inner; p += kIterElems) {
             const int nv = valid4<VEC>(p, a.n_inner);
             const float4 v = load4<VEC>(xr, p, a.n_inner);
@@ -78,6 +79,7 @@ fq_wrow_fwd_kernel(const float *__restrict__ w, float *__restrict__ wq, WRowArgs
             q.lo = -INFINITY;
             q.hi = INFINITY;
             float *yr = wq + row * a.n_inner;
+#pragma unroll 4
             for (int64_t p = (int64_t)tid * 4; p < a.n_inner; p += kIterElems) {
                 const float4 v = load4<VEC>(xr, p, a.n_inner);
                 float4 y;
@@ -143,7 +145,7 @@ fq_wrow_bwd_kernel(const float *__restrict__ go, const float *__restrict__ w, WR
                 }
             }
             const int it0 = (int)(sub & (kSuperSubs - 1)) * kSubIters;
-#pragma unroll 2
+#pragma unroll 4
             for (int it = 0; it < kSubIters; ++it) {
                 const int64_t p = sub * kSubElems + (int64_t)it * kIterElems + tid * 4;
                 const int nv = valid4<VEC>(p, a.n_inner);
