@@ -198,5 +198,78 @@ def main():
          codes=t2n(codes), gx=t2n(xr.grad), g_scale=t2n(scale.grad), g_zp=t2n(zp.grad))
 
 
+def step_fixture():
+    """One whole loss evaluation + backward of a two-layer quantized model through the reference's
+    layers, ModelHelper.get_model_values (utils/model_helper.py:11-76) and PotentialLoss
+    (gdnsq_loss.py:6-88): pins rows (f)-1 of SURVEY.md §8 — the range term
+    log2(max - min + 2^log_wght_s), the constraint loss, and how autograd accumulates the
+    parameter gradients across the three users of every scale."""
+    from collections import OrderedDict
+    gdnsq, gact, gconv, glin, QNMethod, QScheme = import_reference()
+    for name, sub in [("src.quantization.gdnsq.utils", "src/quantization/gdnsq/utils")]:
+        m = types.ModuleType(name)
+        m.__path__ = [os.path.join(REF, sub)]
+        sys.modules[name] = m
+    from src.quantization.gdnsq.utils.model_helper import ModelHelper
+    from src.quantization.gdnsq.gdnsq_loss import PotentialLoss
+    nn = torch.nn
+    g = torch.Generator().manual_seed(400)
+
+    def block(cin, cout, signed, bias):
+        return nn.Sequential(OrderedDict([
+            ("activations_quantizer", gact.NoisyAct(signed=signed)),
+            ("0", gconv.NoisyConv2d(cin, cout, 3, padding=1, bias=bias, qscheme=QScheme.PER_CHANNEL,
+                                    qnmethod=QNMethod.LSQ))]))
+    model = nn.Sequential(OrderedDict([("c1", block(3, 8, True, True)), ("relu", nn.ReLU()),
+                                       ("c2", block(8, 4, False, False))]))
+    # integer-valued log parameters: exp2 is exact on every device
+    act_params = {"c1": (-3.0, 2.0, -2.0), "c2": (-2.0, 1.0, 0.0)}     # log_act_s, log_act_q, act_b
+    with torch.no_grad():
+        for k, (ls, lq, b) in act_params.items():
+            a = getattr(model, k).activations_quantizer
+            a.log_act_s.fill_(ls); a.log_act_q.fill_(lq); a.act_b.fill_(b)
+        for k in ("c1", "c2"):
+            conv = getattr(model, k)._modules["0"]
+            conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.2)
+            conv.weight[0, 0, 0, 0] = conv.weight[0].min()         # tie at a row minimum
+            conv.weight[1, 0, 1, 1] = conv.weight[1].max()         # tie at a row maximum
+            if conv.bias is not None:
+                conv.bias.copy_(torch.randn(conv.bias.shape, generator=g) * 0.05)
+            rng = conv.weight.amax((1, 2, 3), keepdim=True) - conv.weight.amin((1, 2, 3), keepdim=True)
+            conv.log_wght_s.copy_(torch.floor(torch.log2(rng / (2 ** 6 - 1))))   # ~6-7 bits, integer log
+    x = torch.randn(2, 3, 10, 10, generator=g)
+    target = torch.randn(2, 4, 10, 10, generator=g)
+    crit = PotentialLoss(nn.MSELoss(), p=1, a=4, w=4)
+    crit.t, crit.loss_sum, crit.cnt = 0.5, 0.8, 2          # calib_mul = 0.4: constraint term is live
+    model.train(); crit.train()
+    draws = []
+    orig = torch.randint_like
+    gen = torch.Generator().manual_seed(77)
+
+    def rec(t, high, **kw):
+        r = torch.randint(0, 2, t.shape, generator=gen).to(t.dtype)
+        draws.append(r.clone())
+        return r
+    torch.randint_like = rec
+    try:
+        out = model(x)
+        vals = ModelHelper.get_model_values(model, QScheme.PER_CHANNEL)
+        loss = crit((out, *vals), target)
+        loss.backward()
+    finally:
+        torch.randint_like = orig
+    noise = {tuple(d.shape): d for d in draws}
+    arrs = dict(x=t2n(x), target=t2n(target), out=t2n(out), loss=t2n(loss), wloss=t2n(crit.wloss),
+                aloss=t2n(crit.aloss), log_act_s=t2n(vals[0]), log_act_q=t2n(vals[1]),
+                log_wght_s=t2n(vals[2]), log_w_n_b=t2n(vals[3]),
+                noise_bits_c1=t2n(noise[(2, 3, 10, 10)]), noise_bits_c2=t2n(noise[(2, 8, 10, 10)]))
+    for n_, p_ in model.named_parameters():
+        arrs["p:" + n_] = t2n(p_)
+        if p_.grad is not None:
+            arrs["g:" + n_] = t2n(p_.grad)
+    save("step_pc_lsq", **arrs)
+
+
 if __name__ == "__main__":
     main()
+    step_fixture()

@@ -400,3 +400,67 @@ def test_autograd_functions_do_not_leak_their_graph():
         del outs, o
         gc.collect()
         assert all(r() is None for r in refs), "an autograd node or one of its outputs survived"
+
+
+def test_whole_step_against_the_live_reference_fixture():
+    """tests/golden/step_pc_lsq.npz (layers + ModelHelper.get_model_values + PotentialLoss run by
+    the LIVE reference on the CPU) reproduced on the GPU by the product's layer wrappers: the
+    log-domain activation kernels, the row-resident weight kernels with their fused range term,
+    ModelHelper and the loss mirror, with the recorded noise draws injected.  The convolutions
+    in between run in cuDNN (fp32, no TF32) and differ from the CPU's in the last bits, so the
+    downstream quantities are held to 2e-4 instead of bit-exact."""
+    from collections import OrderedDict
+    from mhaq_b200 import ops
+    from mhaq_b200.aux.types import QScheme
+    from mhaq_b200.quantization.gdnsq.gdnsq_loss import PotentialLoss
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_act import NoisyAct
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
+    from mhaq_b200.quantization.gdnsq.utils.model_helper import ModelHelper
+    c = H.load_golden("step_pc_lsq", "cuda")
+
+    def block(cin, cout, signed, bias):
+        return nn.Sequential(OrderedDict([
+            ("activations_quantizer", NoisyAct(signed=signed)),
+            ("0", NoisyConv2d(cin, cout, 3, padding=1, bias=bias, qscheme=QScheme.PER_CHANNEL,
+                              qnmethod=QNMethod.LSQ))]))
+    model = nn.Sequential(OrderedDict([("c1", block(3, 8, True, True)), ("relu", nn.ReLU()),
+                                       ("c2", block(8, 4, False, False))])).cuda()
+    missing = model.load_state_dict({k[2:]: v for k, v in c.items() if k.startswith("p:")}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys       # same state-dict layout
+    noise = {tuple(c[k].shape): H.bits_to_noise(c[k]) for k in ("noise_bits_c1", "noise_bits_c2")}
+    real = ops.act_fake_quant
+
+    def with_recorded_noise(x, log_act_s, log_act_q, act_b, method="STE", noise_=None, philox=None):
+        return real(x, log_act_s, log_act_q, act_b, method=method, noise=noise[tuple(x.shape)])
+
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    ops.act_fake_quant = with_recorded_noise
+    try:
+        model.train()
+        out = model(c["x"])
+        vals = ModelHelper.get_model_values(model, QScheme.PER_CHANNEL)
+        crit = PotentialLoss(nn.MSELoss(), p=1, a=4, w=4)
+        loss = H.step_case_loss(crit, out, vals, c["target"])
+        loss.backward()
+    finally:
+        ops.act_fake_quant = real
+        torch.backends.cudnn.allow_tf32 = tf32
+    for v, k in zip(vals, ("log_act_s", "log_act_q", "log_wght_s")):
+        assert_bit_exact(v, c[k], k)
+    assert_close_rel(vals[3], c["log_w_n_b"], 1e-6, "log_w_n_b", abs_floor=1e-6)
+    assert_close_rel(out, c["out"], 2e-4, "model output", abs_floor=2e-5)
+    assert_close_rel(loss, c["loss"], 1e-5, "loss")
+    assert_close_rel(crit.wloss, c["wloss"], 1e-6, "wloss")
+    assert_close_rel(crit.aloss, c["aloss"], 1e-6, "aloss")
+    n = 0
+    for k, g in c.items():
+        if k.startswith("g:"):
+            p = dict(model.named_parameters())[k[2:]]
+            assert p.grad is not None, k
+            scale = float(g.abs().max())
+            assert_close_rel(p.grad, g, 2e-4, k, abs_floor=2e-4 * scale + 1e-7)
+            n += 1
+    assert n == 10
+    assert model.c1._modules["0"].log_b_s.grad is None

@@ -69,3 +69,42 @@ def test_ewgs_intent_runs():
     # total grad to v = grad of (round(v) - v) path only here: -|g| * e * 0.01
     assert torch.equal(v.grad, -torch.abs(g) * e * 1e-2)
     torch.testing.assert_close(s.grad, ((3.0 ** -0.5) * g * r).sum().reshape(1))
+
+
+def test_whole_step_golden_oracle_and_loss_mirror():
+    """tests/golden/step_pc_lsq.npz — layers + ModelHelper.get_model_values + PotentialLoss of the
+    live reference on a two-convolution model: the oracle's restatement of the layers and the
+    product's PotentialLoss mirror (plain torch, device-agnostic) reproduce the loss and every
+    parameter gradient, including how autograd sums the three uses of each weight scale."""
+    from torch import nn
+    from mhaq_b200.quantization.gdnsq.gdnsq_loss import PotentialLoss
+    c = H.load_golden("step_pc_lsq")
+    # like the generator: the CPU convolution's weight-gradient reduction order depends on the
+    # thread count, and d/d log_wght_s amplifies that last-bit noise (nearly cancelling sums)
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        _whole_step_checks(c, PotentialLoss, nn)
+    finally:
+        torch.set_num_threads(threads)
+
+
+def _whole_step_checks(c, PotentialLoss, nn):
+    P, out, vals = H.run_step_case_oracle(c)
+    H.assert_bit_exact(out, c["out"], "model output")
+    for v, k in zip(vals, ("log_act_s", "log_act_q", "log_wght_s", "log_w_n_b")):
+        H.assert_bit_exact(v, c[k], k)
+    crit = PotentialLoss(nn.MSELoss(), p=1, a=4, w=4)
+    loss = H.step_case_loss(crit, out, vals, c["target"])
+    H.assert_close_rel(loss, c["loss"], 1e-6, "loss")
+    H.assert_close_rel(crit.wloss, c["wloss"], 1e-6, "wloss")
+    H.assert_close_rel(crit.aloss, c["aloss"], 1e-6, "aloss")
+    assert float(crit.cnt) == 3 and abs(float(crit.loss_sum) - (0.8 + crit.rloss.item())) < 1e-6
+    loss.backward()
+    n = 0
+    for k, g in c.items():
+        if k.startswith("g:"):
+            H.assert_close_rel(P[k[2:]].grad, g, 1e-6, k, abs_floor=1e-7)
+            n += 1
+    assert n == 10
+    assert P["c1.0.log_b_s"].grad is None and P["c2.activations_quantizer.act_b"].grad is None
