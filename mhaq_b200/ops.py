@@ -235,6 +235,7 @@ class _Launch:
     """Flattened, validated launch description shared by forward and backward."""
 
     mode = PARAMS_LINEAR
+    stats_over_all = False
 
     def __init__(self, x, scale, zp, lo, hi):
         _require_cuda(x)
@@ -245,6 +246,13 @@ class _Launch:
         self.hi, self.hs = _prep_param(hi, x, "hi")
         if self.scale is None or self.zp is None:
             raise RuntimeError("scale and zero_point are required")
+        # Reference quirk: QNAEWGS averages its statistics over the dims where the scale has
+        # size 1 (reduce_to_shape, gdnsq.py:150-152).  A per-channel scale WITHOUT singleton
+        # dims — the quantized bias: value (O,), scale (O,) (gdnsq_conv2d.py:86-94) — gives an
+        # empty dim tuple, and torch.mean(dim=()) reduces over everything: the statistics are
+        # then per TENSOR although scale / zero point stay per channel.
+        self.stats_over_all = (torch.is_tensor(scale) and scale.dim() > 0 and scale.numel() > 1
+                               and all(n != 1 for n in scale.shape))
 
     @classmethod
     def act_log(cls, x, log_act_s, log_act_q, act_b):
@@ -323,6 +331,10 @@ def aewgs_stats(go, x, L: _Launch, code_grad: bool) -> torch.Tensor:
     check(lib.mhaq_fq_aewgs_stats_finalize_f32(_ptr(ws), geo.n_rows, geo.n_inner, geo.n_ch,
                                                _ptr(stats), _stream()),
           "mhaq_fq_aewgs_stats_finalize_f32")
+    if L.stats_over_all and geo.n_ch > 1:
+        # channels hold equally many elements, so the mean over everything is the mean of the
+        # channel means; every channel then uses the same (num, e2, me)
+        stats = stats.view(3, geo.n_ch).mean(dim=1, keepdim=True).expand(3, geo.n_ch).reshape(-1).contiguous()
     return allreduce_packed_stats(stats)
 
 

@@ -464,3 +464,39 @@ def test_whole_step_against_the_live_reference_fixture():
             n += 1
     assert n == 10
     assert model.c1._modules["0"].log_b_s.grad is None
+
+
+@pytest.mark.parametrize("method", ["STE", "LSQ", "AEWGS"])
+def test_noisy_conv_quantized_bias_reuses_weight_scale_and_row_min(method):
+    """quant_bias=True (per-channel only): the bias is quantized with the weight's scale and
+    row minimum, ravelled (gdnsq_conv2d.py:86-94) — here on top of the fused weight routes,
+    whose operands the Quantizer materialises lazily."""
+    from mhaq_b200.aux.types import QScheme
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
+    torch.manual_seed(2)
+    conv = NoisyConv2d(8, 16, 3, padding=1, bias=True, qscheme=QScheme.PER_CHANNEL, quant_bias=True,
+                       qnmethod=QNMethod[method]).cuda()
+    with torch.no_grad():
+        conv.weight.mul_(2.0)
+        conv.bias.copy_(torch.randn(16) * 0.1)
+        conv.log_wght_s.fill_(-4.0)
+    conv.train()
+    wq, bq = conv.quantized_weight()
+    gw, gb = torch.randn(wq.shape), torch.randn(16)
+    ((wq * gw.cuda()).sum() + (bq * gb.cuda()).sum()).backward()
+    w = conv.weight.detach().cpu().clone().requires_grad_(True)
+    b = conv.bias.detach().cpu().clone().requires_grad_(True)
+    ls = conv.log_wght_s.detach().cpu().clone().requires_grad_(True)
+    z = torch.zeros_like
+    wo = O.weight_fake_quant(w, ls, True, method, noise=z(w))
+    bo = O.bias_fake_quant(b, w, ls, method, noise=z(b))
+    ((wo * gw).sum() + (bo * gb).sum()).backward()
+    assert_bit_exact(wq, wo, "wq")
+    assert_bit_exact(bq, bo, "bq")
+    if method == "LSQ":      # (STE / AEWGS: the scale gradient carries the in-kernel noise term)
+        assert_close_rel(conv.log_wght_s.grad, ls.grad, 1e-5, "g_log_wght_s", abs_floor=5e-5)
+    if method != "AEWGS":
+        assert_close_rel(conv.bias.grad, b.grad, 1e-5, "g_bias", abs_floor=1e-6)
+    assert_close_rel(conv.weight.grad, w.grad, 1e-5, "g_weight", abs_floor=3e-5)
+    assert conv.log_b_s.grad is None          # never used, exactly like the reference (quirk 5)
