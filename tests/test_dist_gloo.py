@@ -99,3 +99,62 @@ def test_bench_reference_arm_under_torchrun_two_ranks():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "GB/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+class _ToyQuantLayer(torch.nn.Module):
+    """Parameter layout of a per-channel NoisyConv2d as DDP sees it: used weight + scale, and a
+    trainable `log_b_s` that never takes part in the forward."""
+
+    def __init__(self):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.randn(4, 3))
+        self.log_wght_s = torch.nn.Parameter(torch.full((4, 1), -2.0))
+        self.log_b_s = torch.nn.Parameter(torch.full((1,), -12.0))
+
+    def forward(self, x):
+        return x @ (self.weight * torch.exp2(self.log_wght_s)).t()
+
+
+def _ddp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, ROOT)
+        from mhaq_b200 import harness
+        torch.manual_seed(0)                       # identical replicas
+        model = torch.nn.Sequential(_ToyQuantLayer(), torch.nn.ReLU(), torch.nn.Linear(4, 2))
+        ddp = harness.wrap_ddp(model, None, lean=True)
+        opt = torch.optim.SGD([p for p in model.parameters()], lr=0.1)
+        g = torch.Generator().manual_seed(10 + rank)     # different data per rank
+        for _ in range(3):                         # would raise on step 2 if log_b_s were not ignored
+            x = torch.randn(8, 3, generator=g)
+            ddp(x).square().mean().backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        # the replicas-in-sync check of bench.py's QAT leg
+        chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        unused_grad_none = model[0].log_b_s.grad is None
+        q.put((rank, bool((lo == hi).item()), unused_grad_none, float(model[0].log_b_s.detach())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_lean_ddp_wrapping_ignores_the_never_used_log_b_s():
+    """harness.wrap_ddp(lean=True): no find_unused_parameters graph walk — the unused `log_b_s`
+    parameters are excluded from DDP's reducer instead; replicas stay in sync."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, in_sync, unused_none, lbs in res:
+        assert in_sync, f"rank {rank}: replicas diverged"
+        assert unused_none and lbs == -12.0
