@@ -24,9 +24,6 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .quantization.gdnsq.layers.gdnsq_act import NoisyAct
-from .quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
-from .quantization.gdnsq.layers.gdnsq_linear import NoisyLinear
 
 
 class LModule(nn.Module):

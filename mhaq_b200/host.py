@@ -16,7 +16,6 @@ device in chunk order (deterministic).
 from __future__ import annotations
 
 import math
-from typing import Optional
 
 import torch
 

@@ -14,7 +14,6 @@ from typing import Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-from . import _lib
 from ._lib import lib, check
 
 METHOD_IDS = {"STE": 0, "EWGS": 1, "AEWGS": 2, "LSQ": 3}

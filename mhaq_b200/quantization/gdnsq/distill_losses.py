@@ -1,6 +1,5 @@
 """Distillation criteria selectable by ``quantization.params.distillation_loss``
 (reference: src/aux/loss/*.py, gdnsq_quant.py:40-66).  Logits-sized, plain PyTorch."""
-import torch
 import torch.nn.functional as F
 from torch import nn
 

@@ -7,8 +7,6 @@ per-channel and — exactly as in the reference — is never used (bias quantiza
 reuses the weight scale / row minimum, gdnsq_conv2d.py:86-94); ``_noise_ratio`` is
 a non-trainable ``(1,)`` Parameter kept for state-dict compatibility.
 """
-from typing import Tuple
-
 import torch
 from torch import nn, inf
 

@@ -10,7 +10,6 @@ import socket
 import subprocess
 import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

@@ -1,5 +1,5 @@
 """Host cost of one fake_quant forward / backward call (small tensor: GPU time negligible)."""
-import cProfile, pstats, io, sys, os, time, math, torch
+import cProfile, pstats, io, sys, os, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import mhaq_b200
 from mhaq_b200 import ops

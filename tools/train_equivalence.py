@@ -3,7 +3,7 @@
 chain (oracle port) on the same GPU.  Same init, same batches, deterministic cuDNN, TF32 off.
 Bit-exact forward + bit-exact input gradients => the trajectories coincide until fp32
 summation-order noise in the (tiny) scale gradients is amplified by training."""
-import os, sys, copy, torch
+import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
