@@ -117,3 +117,32 @@ def test_plain_c_client_links_and_runs(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "abi_client OK" in r.stdout
+
+
+def _header_param_counts():
+    src = open(os.path.join(ROOT, "include", "mhaq_fq.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(mhaq_fq_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_binding_arities_match_the_header():
+    """Every ctypes signature in mhaq_b200/_lib.py — and the maintainer-side stub printed in
+    INTEGRATION.md — has exactly as many arguments as the C declaration."""
+    from mhaq_b200 import _lib
+    counts = _header_param_counts()
+    assert set(counts) == set(_lib.EXPORTED_SYMBOLS)
+    for name, (_, argtypes) in _lib._SIGNATURES.items():
+        assert len(argtypes) == counts[name], f"{name}: binding {len(argtypes)} vs header {counts[name]}"
+    # the stub of INTEGRATION.md section C, executed against the built library
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(import ctypes, torch\n.*?)\ndef fake_quant_fwd", md, flags=re.S).group(1)
+    block = block.replace('ctypes.CDLL("libmhaq_fq.so")', f'ctypes.CDLL({_lib.LIB_PATH!r})')
+    ns = {}
+    exec(block, ns)
+    for fn in ("mhaq_fq_fwd_f32", "mhaq_fq_bwd_f32", "mhaq_fq_bwd_finalize_f32", "mhaq_fq_workspace_bytes"):
+        assert len(getattr(ns["L"], fn).argtypes) == counts[fn], f"INTEGRATION.md stub: {fn}"
+    assert (ns["LINEAR"], ns["ACT_LOG"], ns["WEIGHT_LOG"]) == (0, 1, 2)
