@@ -63,7 +63,12 @@ def t2n(t):
     return None if t is None else t.detach().cpu().numpy()
 
 
+ONLY = set(sys.argv[1:])     # optional: names of the fixtures to (re)write; default all
+
+
 def save(name, **arrs):
+    if ONLY and name not in ONLY:
+        return
     arrs = {k: v for k, v in arrs.items() if v is not None}
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
     print(f"  {name}: " + ", ".join(f"{k}{tuple(np.shape(v))}" for k, v in arrs.items()))
@@ -126,6 +131,11 @@ def main():
         ("w_pt_ste", "PER_TENSOR", "STE", (8, 4, 3, 3), 4, False),
         ("w_pt_lsq", "PER_TENSOR", "LSQ", (5, 3, 3, 3), 2, False),
         ("w_pc_ste_bias", "PER_CHANNEL", "STE", (8, 4, 3, 3), 4, True),
+        # quantized bias under AEWGS: value (O,), scale (O,) -> reduce_to_shape has no singleton
+        # dim, torch.mean(dim=()) reduces over everything: per-TENSOR statistics for the bias
+        ("w_pc_aewgs_bias", "PER_CHANNEL", "AEWGS", (8, 4, 3, 3), 2, True),
+        # per-tensor AEWGS: scale (1,) -> statistics over dim 0 only
+        ("w_pt_aewgs", "PER_TENSOR", "AEWGS", (6, 4, 3, 3), 3, False),
     ]
     for i, (name, scheme, method, shape, bits_w, qbias) in enumerate(w_cases):
         g = torch.Generator().manual_seed(200 + i)
@@ -272,4 +282,5 @@ def step_fixture():
 
 if __name__ == "__main__":
     main()
-    step_fixture()
+    if not ONLY or "step_pc_lsq" in ONLY:
+        step_fixture()
