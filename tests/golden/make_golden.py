@@ -191,6 +191,22 @@ def main():
              g_bias=t2n(conv.bias.grad) if qbias else None,
              per_channel=np.bool_(scheme == "PER_CHANNEL"), method=np.str_(method))
 
+    # ---------------- NoisyLinear, per-tensor (the only usable scheme) -------
+    g = torch.Generator().manual_seed(250)
+    lin = glin.NoisyLinear(20, 12, bias=True, qscheme=QScheme.PER_TENSOR, qnmethod=QNMethod.LSQ)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(12, 20, generator=g) * 0.3)
+        lin.bias.copy_(torch.randn(12, generator=g) * 0.1)
+        lin.log_wght_s.fill_(float(torch.log2((lin.weight.max() - lin.weight.min()) / (2 ** 4 - 1))))
+    lin.train()
+    xl = torch.randn(5, 20, generator=g).requires_grad_(True)
+    gol = torch.randn(5, 12, generator=g)
+    yl = lin(xl)
+    yl.backward(gol)
+    save("lin_pt_lsq", weight=t2n(lin.weight), bias=t2n(lin.bias), log_wght_s=t2n(lin.log_wght_s),
+         x=t2n(xl), go=t2n(gol), y=t2n(yl), gx=t2n(xl.grad), g_weight=t2n(lin.weight.grad),
+         g_bias=t2n(lin.bias.grad), g_log_wght_s=t2n(lin.log_wght_s.grad))
+
     # ---------------- raw Quantizer with explicit tensors (two-call API) ----------------------
     g = torch.Generator().manual_seed(300)
     x = torch.randn(4, 6, 5, 5, generator=g)

@@ -500,3 +500,28 @@ def test_noisy_conv_quantized_bias_reuses_weight_scale_and_row_min(method):
         assert_close_rel(conv.bias.grad, b.grad, 1e-5, "g_bias", abs_floor=1e-6)
     assert_close_rel(conv.weight.grad, w.grad, 1e-5, "g_weight", abs_floor=3e-5)
     assert conv.log_b_s.grad is None          # never used, exactly like the reference (quirk 5)
+
+
+def test_noisy_linear_against_the_live_reference_fixture():
+    """tests/golden/lin_pt_lsq.npz: NoisyLinear per-tensor LSQ run by the live reference."""
+    from mhaq_b200.aux.types import QScheme
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_linear import NoisyLinear
+    c = H.load_golden("lin_pt_lsq", "cuda")
+    lin = NoisyLinear(20, 12, bias=True, qscheme=QScheme.PER_TENSOR, qnmethod=QNMethod.LSQ).cuda()
+    with torch.no_grad():
+        lin.weight.copy_(c["weight"]); lin.bias.copy_(c["bias"]); lin.log_wght_s.copy_(c["log_wght_s"])
+    lin.train()
+    x = c["x"].clone().requires_grad_(True)
+    wq = lin.quantized_weight()
+    y = lin(x)
+    y.backward(c["go"])
+    w_ref = O.weight_fake_quant(c["weight"].cpu(), c["log_wght_s"].cpu(), False, "LSQ")
+    # forward codes can only differ where CUDA's exp2f and the CPU's exp2 differ in the last bit
+    # of the scale: compare the dequantized weight loosely, everything downstream at 1e-4
+    assert_close_rel(wq, w_ref, 1e-5, "wq", abs_floor=1e-6)
+    assert_close_rel(y, c["y"], 1e-4, "y", abs_floor=1e-5)
+    assert_close_rel(x.grad, c["gx"], 1e-4, "gx", abs_floor=1e-5)
+    assert_close_rel(lin.weight.grad, c["g_weight"], 1e-4, "g_weight", abs_floor=2e-5)
+    assert_close_rel(lin.bias.grad, c["g_bias"], 1e-5, "g_bias", abs_floor=1e-6)
+    assert_close_rel(lin.log_wght_s.grad, c["g_log_wght_s"], 1e-3, "g_log_wght_s", abs_floor=1e-4)

@@ -108,3 +108,20 @@ def _whole_step_checks(c, PotentialLoss, nn):
             n += 1
     assert n == 10
     assert P["c1.0.log_b_s"].grad is None and P["c2.activations_quantizer.act_b"].grad is None
+
+
+def test_noisy_linear_golden():
+    """NoisyLinear.forward, per-tensor LSQ (gdnsq_linear.py:61-78), run by the live reference."""
+    import torch.nn.functional as F
+    c = H.load_golden("lin_pt_lsq")
+    w = c["weight"].clone().requires_grad_(True)
+    b = c["bias"].clone().requires_grad_(True)
+    ls = c["log_wght_s"].clone().requires_grad_(True)
+    x = c["x"].clone().requires_grad_(True)
+    y = F.linear(x, O.weight_fake_quant(w, ls, False, "LSQ"), b)
+    y.backward(c["go"])
+    H.assert_bit_exact(y, c["y"], "y")
+    H.assert_bit_exact(x.grad, c["gx"], "gx")
+    H.assert_close_rel(w.grad, c["g_weight"], 1e-6, "g_weight", abs_floor=1e-7)
+    H.assert_close_rel(b.grad, c["g_bias"], 1e-6, "g_bias", abs_floor=1e-7)
+    H.assert_close_rel(ls.grad, c["g_log_wght_s"], 1e-6, "g_log_wght_s", abs_floor=1e-7)
