@@ -2,7 +2,7 @@
 """bench.py — fake-quant fwd+bwd throughput (BASELINE.json metric) on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]           # our sm_100a path
-    python bench.py --impl reference [...]                        # reference CPU path (oracle port)
+    python bench.py --impl reference [...]                        # the LIVE reference's CPU path (oracle/_ref)
 
 A "step" is one pass of the hot path over one batch of synthetic input: one
 fake-quant forward + one backward (incl. the in-kernel deterministic reduction) over a
@@ -46,20 +46,25 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also run the config-2 sweep -> gpurun_out/")
-    ap.add_argument("--cpu-log2n", type=int, default=24)
-    ap.add_argument("--no-resnet", action="store_true", help="skip the ResNet-18 W4A4 QAT leg")
-    ap.add_argument("--resnet-batch", type=int, default=256, help="per-GPU batch (config 4)")
+    ap.add_argument("--cpu-log2n", type=int, default=26,
+                    help="elements per step of the CPU reference sample (SURVEY.md §8d: N capped at 2^26)")
+    ap.add_argument("--no-resnet", action="store_true", help="skip the QAT legs (configs[2..4])")
+    ap.add_argument("--qat-legs", default="resnet18,resnet20,rfdn",
+                    help="which QAT legs the default line carries: resnet18 = configs[3] STE W4A4 b256, "
+                         "resnet20 = configs[2] AEWGS W1A1 b256, rfdn = configs[4] LSQ W2A2 b16")
+    ap.add_argument("--no-graph-microbench", action="store_true",
+                    help="launch the microbench step from Python instead of replaying its CUDA graph")
+    ap.add_argument("--resnet-batch", type=int, default=None, help="override the per-GPU batch of the QAT legs")
     ap.add_argument("--resnet-steps", type=int, default=12)
-    ap.add_argument("--qat-model", default="resnet18", choices=["resnet18", "resnet20", "rfdn"],
-                    help="resnet18 = configs[3] (ImageNet-shaped, STE W4A4); resnet20 = configs[2] "
-                         "(CIFAR-100-shaped; use --qat-method AEWGS --qat-bits 1); rfdn = configs[4] "
-                         "(x4 super-resolution on 256x256 patches, L1, no teacher; use --qat-method LSQ "
-                         "--qat-bits 2 --resnet-batch 16)")
-    ap.add_argument("--qat-method", default="STE", choices=["STE", "LSQ", "AEWGS", "EWGS"])
-    ap.add_argument("--qat-bits", type=int, default=4)
+    ap.add_argument("--qat-model", default=None, choices=["resnet18", "resnet20", "rfdn"],
+                    help="run ONE custom QAT leg instead of --qat-legs (combine with --qat-method / --qat-bits)")
+    ap.add_argument("--qat-method", default=None, choices=["STE", "LSQ", "AEWGS", "EWGS"])
+    ap.add_argument("--qat-bits", type=int, default=None)
     ap.add_argument("--ddp-reference-flags", action="store_true",
-                    help="wrap DDP exactly like the reference's Trainer (find_unused_parameters=True, "
-                         "buffer broadcast every step) instead of the lean wrapping")
+                    help="N > 1: run the main QAT legs with the reference Trainer's flags (SyncBatchNorm, "
+                         "find_unused_parameters=True, buffer broadcast; training/trainer.py:88-97,166), eagerly "
+                         "launched, instead of the lean graph-captured wrapping.  (The default N > 1 line carries "
+                         "one such ResNet-18 row beside the lean one.)")
     ap.add_argument("--graph", action="store_true", default=True, help=argparse.SUPPRESS)
     ap.add_argument("--no-graph", dest="graph", action="store_false",
                     help="QAT leg: launch the training step eagerly from Python.  Default: the whole step "
@@ -167,8 +172,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def time_region(fn, steps, sync_dist):
-    """K steps between barrier+synchronize on both sides, CUDA events on the launching stream."""
+def time_region(fn, steps, sync_dist, per_rank=None):
+    """K steps between barrier+synchronize on both sides, CUDA events on the launching stream;
+    returns the MAX over ranks (ms for the K steps).  `per_rank`: list that receives every rank's
+    own time."""
     import torch.distributed as dist
     torch.cuda.synchronize()
     if sync_dist:
@@ -185,96 +192,96 @@ def time_region(fn, steps, sync_dist):
     ms = e0.elapsed_time(e1)
     if sync_dist:
         t = torch.tensor([ms], device="cuda")
+        if per_rank is not None:
+            allt = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+            dist.all_gather(allt, t)
+            per_rank.extend(float(v.item()) for v in allt)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    elif per_rank is not None:
+        per_rank.append(ms)
     return ms
 
 
+def bench_config(a):
+    """The workload description — IDENTICAL in both arms (`--impl ours` / `--impl reference`)."""
+    n = 1 << a.log2n
+    return {"workload": workload_name(a), "elements_per_gpu": n,
+            "layout": [a.channels, n // a.channels] if a.channels else [n],
+            "method": a.method, "bits": a.bits, "bytes_per_element": 20,
+            "l2": "inputs (1 GiB each at N=2^28) far exceed the 126 MB L2; no flush needed",
+            "multi_gpu": "replicas only (independent tensors per GPU, no data-path collective)"}
+
+
 # ---------------------------------------------------------------------------
-class _EagerReferenceBackend:
-    """Bench-only A/B switch: route Quantizer.fake_quant through the reference's eager ATen
-    chain (the oracle port) on the GPU, to time the SAME QAT step the way the reference runs
-    it.  Lives in bench.py on purpose — the product has no such switch."""
-
-    def __enter__(self):
-        from mhaq_b200.quantization.gdnsq import gdnsq as G
-        from mhaq_b200 import ops
-        from oracle import fq_oracle as O
-        self.G, self.ops = G, ops
-        self.saved = (G.Quantizer.fake_quant, G.Quantizer.fake_quant_eval, G.Quantizer.fake_quant_weight,
-                      ops.act_fake_quant)
-
-        def fake_quant(q, value, noise=None):
-            return O.fake_quant(value, q.scale, q.zero_point, q.min_val, q.max_val,
-                                method=q.qnmethod.name, noise=noise)
-
-        def fake_quant_eval(q, value):
-            codes = O.quantize(value, q.scale, q.zero_point, q.min_val, q.max_val)
-            mm = codes.aminmax()
-            return O.dequantize(codes, q.scale, q.zero_point), torch.stack(
-                [mm.min, mm.max, torch.zeros((), device=value.device)])
-
-        def fake_quant_weight(q, weight, log_scale=None, noise=None):
-            # NoisyConv2d.forward's weight lines (gdnsq_conv2d.py:72-84,98) op for op; no row
-            # range is returned, so ModelHelper re-reduces the weight like the reference does
-            if log_scale is not None:
-                q.scale = torch.exp2(log_scale)
-            q.zero_point = weight.amin(tuple(range(1, weight.dim())), keepdim=True)
-            wq = O.fake_quant(weight, q.scale, q.zero_point, -math.inf, math.inf,
-                              method=q.qnmethod.name, noise=noise)
-            return wq, None, None, None
-
-        def act_fake_quant(x, log_act_s, log_act_q, act_b, method="STE", noise=None, philox=None):
-            return O.act_fake_quant(x, log_act_s, log_act_q, act_b, noise=noise, method=method)
-
-        G.Quantizer.fake_quant, G.Quantizer.fake_quant_eval = fake_quant, fake_quant_eval
-        G.Quantizer.fake_quant_weight = fake_quant_weight
-        ops.act_fake_quant = act_fake_quant
-        return self
-
-    def __exit__(self, *a):
-        G = self.G
-        (G.Quantizer.fake_quant, G.Quantizer.fake_quant_eval, G.Quantizer.fake_quant_weight,
-         self.ops.act_fake_quant) = self.saved
+QAT_LEGS = {
+    "resnet18": dict(model="resnet18", method="STE", bits=4, batch=256, key="resnet18_w4a4_qat"),
+    "resnet20": dict(model="resnet20", method="AEWGS", bits=1, batch=256, key="resnet20_aewgs_w1a1_qat"),
+    "rfdn": dict(model="rfdn", method="LSQ", bits=2, batch=16, key="rfdn_lsq_w2a2_qat"),
+}
 
 
-def qat_key(a):
-    if (a.qat_model, a.qat_method, a.qat_bits) == ("resnet18", "STE", 4):
-        return "resnet18_w4a4_qat"
-    return f"{a.qat_model}_{a.qat_method.lower()}_w{a.qat_bits}a{a.qat_bits}_qat"
+def qat_specs(a):
+    if a.qat_model:
+        spec = dict(QAT_LEGS[a.qat_model])
+        names = [a.qat_model]
+        QATS = {a.qat_model: spec}
+    else:
+        names = [n for n in a.qat_legs.split(",") if n]
+        QATS = {n: dict(QAT_LEGS[n]) for n in names}
+    out = []
+    for n in names:
+        s = QATS[n]
+        if a.qat_method:
+            s["method"] = a.qat_method
+        if a.qat_bits:
+            s["bits"] = a.qat_bits
+        if a.resnet_batch:
+            s["batch"] = a.resnet_batch
+        if (s["model"], s["method"], s["bits"]) != tuple(QAT_LEGS[n][k] for k in ("model", "method", "bits")):
+            s["key"] = f"{s['model']}_{s['method'].lower()}_w{s['bits']}a{s['bits']}_qat"
+        out.append(s)
+    return out
 
 
-def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
-    """BASELINE configs[3]: torchvision ResNet-18, ImageNet-shaped synthetic batch (256 per GPU,
-    224x224), GDNSQ/STE W4A4 per-channel, distillation (Symmetrical KL) from a frozen FP copy,
-    RAdam lr 3e-4, fp32 + TF32 convolutions, DDP over NCCL for N > 1 — through
-    Quantizer(config)().quantize(lmodel) and the patched training_step."""
-    from mhaq_b200 import harness
+def qat_leg(a, dev, world, rank, use_dist, spec, ref_flags=False, profile_share=True):
+    """One QAT leg (BASELINE configs[2..4]) through Quantizer(config)().quantize(lmodel) and the
+    patched training_step: synthetic batch per GPU, RAdam, fp32 + TF32 convolutions, DDP over NCCL
+    for N > 1.  configs[3]: torchvision ResNet-18, 224x224, GDNSQ/STE W4A4 per-channel, Symmetrical-KL
+    distillation from a frozen FP copy.  configs[2]: CIFAR ResNet-20 (100 classes), AEWGS W1A1 (the
+    config with a data-path collective: AEWGS's in-backward statistics all-reduce).  configs[4]: RFDN
+    x4 on 256x256 LR patches, LSQ W2A2, L1, no teacher.  `ref_flags`: the reference Trainer's DDP
+    flags (SyncBatchNorm, find_unused_parameters=True, buffer broadcast), eagerly launched."""
+    from mhaq_b200 import harness, ops
     torch.backends.cudnn.benchmark = True
     torch.set_float32_matmul_precision("high")
-    B = a.resnet_batch
+    model_name, method, bits, B = spec["model"], spec["method"], spec["bits"], spec["batch"]
+    graph = a.graph and not ref_flags
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    sr = a.qat_model == "rfdn"
+    sr = model_name == "rfdn"
     if sr:      # LR patch in [0,1] (denormalised x255 inside the module), HR target x4
         x = torch.rand(B, 3, 256, 256, device=dev, generator=g)
         t = torch.rand(B, 3, 1024, 1024, device=dev, generator=g)
-        q = harness.build_qat("rfdn", dev, qnmethod=a.qat_method, act_bit=a.qat_bits, weight_bit=a.qat_bits,
-                              distillation=False, lr=5e-4, calib_batch=x[: min(B, 4)], calib_bits=a.qat_bits)
+        q = harness.build_qat("rfdn", dev, qnmethod=method, act_bit=bits, weight_bit=bits,
+                              distillation=False, lr=5e-4, calib_batch=x[: min(B, 4)], calib_bits=bits)
     else:
-        side, classes = (224, 1000) if a.qat_model == "resnet18" else (32, 100)
+        side, classes = (224, 1000) if model_name == "resnet18" else (32, 100)
         x = torch.randn(B, 3, side, side, device=dev, generator=g)
         t = torch.randint(0, classes, (B,), device=dev, generator=g)
-        q = harness.build_qat(a.qat_model, dev, qnmethod=a.qat_method, act_bit=a.qat_bits,
-                              weight_bit=a.qat_bits, distillation=True, num_classes=classes,
-                              calib_batch=x[: min(B, 64)])
+        q = harness.build_qat(model_name, dev, qnmethod=method, act_bit=bits, weight_bit=bits,
+                              distillation=True, num_classes=classes, calib_batch=x[: min(B, 64)])
     if a.channels_last:
         q.model.to(memory_format=torch.channels_last)
         if getattr(q, "tmodel", None) is not None:
             q.tmodel.to(memory_format=torch.channels_last)
         x = x.contiguous(memory_format=torch.channels_last)
     if use_dist:
-        wrap = harness.ddp_side_stream if a.graph else harness.wrap_ddp
-        q.model = wrap(q.model, dev, lean=not a.ddp_reference_flags)
+        if ref_flags:      # training/trainer.py:88,166 (sync_batchnorm=True) and :92-97
+            q.model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(q.model)
+            if a.channels_last:
+                q.model.to(memory_format=torch.channels_last)
+        wrap = harness.ddp_side_stream if graph else harness.wrap_ddp
+        q.model = wrap(q.model, dev, lean=not ref_flags)
     q.train(); q.wrapped_criterion.train()
     if getattr(q, "tmodel", None) is not None:
         q.tmodel.eval()
@@ -289,7 +296,7 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
 
     res = {}
     k = a.resnet_steps
-    if a.graph and not use_dist:
+    if graph and not use_dist:
         # the same step launched eagerly from Python first: its time, and (CUPTI) which share of
         # the GPU time the fake-quant kernels take — a graph replay hides kernel names from CUPTI
         for _ in range(4):
@@ -303,21 +310,52 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
                 eager_step(); eager_step()
                 torch.cuda.synchronize()
             tot = fq = 0.0
+            nl = nfq = 0
             for ev in prof.key_averages():
                 dt = getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0)
                 tot += dt
+                nl += ev.count
                 if "fq_" in ev.key:
                     fq += dt
+                    nfq += ev.count
             if tot > 0:
                 res["fake_quant_kernel_share"] = round(fq / tot, 4)
                 res["fake_quant_ms_per_step"] = round(fq / 2 / 1e3, 3)
                 res["gpu_kernel_ms_per_step"] = round(tot / 2 / 1e3, 2)   # rest of an eager step = GPU idle
+                res["launches_per_step"] = nl // 2
+                res["fake_quant_launches_per_step"] = nfq // 2
         except Exception as exc:   # profiler unavailable: the throughput numbers stand alone
             res["fake_quant_kernel_share"] = None
             res["profiler_error"] = str(exc)[:80]
+    if use_dist and method == "AEWGS":
+        # the ONE data-path collective (gdnsq.py:126-129, here one packed all-reduce per weight
+        # tensor): its GPU time per step, CUDA events around every call over 3 eager DDP steps
+        evs, orig = [], ops.allreduce_packed_stats
+
+        def timed_allreduce(stats):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = orig(stats)
+            e1.record()
+            evs.append((e0, e1))
+            return out
+
+        for _ in range(2):
+            eager_step()
+        ops.allreduce_packed_stats = timed_allreduce
+        try:
+            for _ in range(3):
+                eager_step()
+            torch.cuda.synchronize()
+        finally:
+            ops.allreduce_packed_stats = orig
+        tot = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+        res["aewgs_stats_allreduce"] = {"calls_per_step": len(evs) // 3, "ms_per_step": round(tot / 3, 3),
+                                        "what": "packed [3,O] AVG all-reduce between the statistics and the apply "
+                                                "kernel, one per AEWGS weight tensor (eager DDP steps, CUDA events)"}
 
     graphed = None
-    if a.graph:
+    if graph:
         # capture; if it fails on ANY rank every rank falls back to eager launches (the bench
         # line must not depend on a capture succeeding) and says so
         note = None
@@ -333,8 +371,7 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
             if graphed is not None:
                 graphed.close()
             graphed = None
-            from mhaq_b200 import ops as _ops
-            _ops.set_device_philox_state(None)
+            ops.set_device_philox_state(None)
             torch.cuda.synchronize()
             opt = q.configure_optimizers()
             res["graph_capture_failed"] = note or "capture failed on another rank"
@@ -356,24 +393,30 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
 
     for _ in range(4):
         step()
-    ms = time_region(step, k, use_dist) / k
+    ranks_ms = []
+    ms = time_region(step, k, use_dist, per_rank=ranks_ms) / k
     ke = max(3, k // 2)
     step_e2e()
     ms_e = time_region(step_e2e, ke, use_dist) / ke
     cfg = {"resnet18": "configs[3] ResNet-18 224x224", "resnet20": "configs[2] ResNet-20 32x32 (CIFAR-100 shaped)",
-           "rfdn": "configs[4] RFDN x4 SR, 256x256 LR patches, L1"}[a.qat_model]
-    res = {"workload": f"{cfg} {a.qat_method} W{a.qat_bits}A{a.qat_bits} QAT, {'no teacher' if sr else 'distillation'}, RAdam, fp32/TF32, "
-                       f"batch {B}/GPU, {'channels_last' if a.channels_last else 'NCHW'}, "
-                       f"{'DDP dp%d' % world if use_dist else 'single GPU'}, "
+           "rfdn": "configs[4] RFDN x4 SR, 256x256 LR patches, L1"}[model_name]
+    par = "single GPU"
+    if use_dist:
+        par = f"DDP dp{world}" + (", reference Trainer flags: SyncBatchNorm + find_unused_parameters=True + buffer "
+                                  "broadcast" if ref_flags else ", lean wrapping (log_b_s ignored, no buffer broadcast)")
+    res = {"workload": f"{cfg} {method} W{bits}A{bits} QAT, {'no teacher' if sr else 'distillation'}, RAdam, fp32/TF32, "
+                       f"batch {B}/GPU, {'channels_last' if a.channels_last else 'NCHW'}, {par}, "
                        f"{'whole step (NCCL all-reduces included) replayed from a CUDA graph' if graphed is not None else 'eager launches'}",
            "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
            "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1),
            "e2e_h2d_bytes_per_step": hx.numel() * hx.element_size() + ht.numel() * ht.element_size(),
            "n_gpus": world,
-           "quantized_act_elems_per_step": {"resnet18": 1680896, "resnet20": 184320, "rfdn": 59093392}[a.qat_model] * B,
+           "quantized_act_elems_per_step": {"resnet18": 1680896, "resnet20": 184320, "rfdn": 59093392}[model_name] * B,
            **res}
     if use_dist:   # replicas must hold identical parameters after the DDP steps
         import torch.distributed as dist
+        rm = sorted(v / k for v in ranks_ms)
+        res["per_rank_ms_per_step"] = {"min": round(rm[0], 3), "median": round(rm[len(rm) // 2], 3), "max": round(rm[-1], 3)}
         chk = torch.stack([p.detach().double().sum() for p in q.model.parameters()]).sum().reshape(1)
         lo_, hi_ = chk.clone(), chk.clone()
         dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
@@ -385,29 +428,46 @@ def resnet18_leg(a, dev, world, rank, use_dist, profile_share=True):
     return res
 
 
-def eager_reference_leg(a, dev):
-    """The reference's own ATen chain (the oracle port, same ops) executed eagerly on the B200:
-    the honest speed-up denominator for the fused kernels."""
-    from oracle import fq_oracle as O
-    b = argparse.Namespace(**vars(a))
-    b.log2n = min(a.log2n, 26)
-    n = 1 << b.log2n
-    x, go, scale, zp, lo, hi = make_inputs(b, dev)
-    lo_ = -math.inf if lo is None else lo
-    hi_ = math.inf if hi is None else hi
-    sp = scale.clone().requires_grad_(True)
+def host_link_probe(dev, use_dist):
+    """What bounds the host-buffer e2e leg: pinned-host <-> device copy bandwidth of THIS rank with every
+    rank copying at the same time (H2D alone, D2H alone, both directions at once) and a plain host
+    memcpy, 256 MiB buffers."""
+    n = 64 << 20
+    h_in = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_out = torch.empty(n, dtype=torch.float32).pin_memory()
+    d_in, d_out = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    by = 4 * n
 
-    def step():
-        xs = x.detach().requires_grad_(True)
-        sp.grad = None
-        y = O.fake_quant(xs, sp, zp, lo_, hi_, method=a.method)
-        y.backward(go)
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        if use_dist:
+            import torch.distributed as dist
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
 
-    for _ in range(3):
-        step()
-    ms = time_region(step, 10, False) / 10
-    return {"value": round(20 * n / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "ms_per_step": round(ms, 3),
-            "what": f"reference ATen op chain (oracle port) run eagerly on this GPU, N=2^{b.log2n}"}
+    def both():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+
+    t_h2d = timed(lambda: d_in.copy_(h_in, non_blocking=True))
+    t_d2h = timed(lambda: h_out.copy_(d_out, non_blocking=True))
+    t_both = timed(both)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        h_out.copy_(h_in)
+    t_mem = (time.perf_counter() - t0) / 2
+    return {"h2d_GBps": round(by / t_h2d / 1e9, 1), "d2h_GBps": round(by / t_d2h / 1e9, 1),
+            "duplex_each_way_GBps": round(by / t_both / 1e9, 1), "host_memcpy_GBps": round(2 * by / t_mem / 1e9, 1),
+            "what": "this rank's pinned-host<->device copies with all ranks copying concurrently; host_memcpy = "
+                    "one thread's read+write bytes/s"}
 
 
 # ---------------------------------------------------------------------------
@@ -433,14 +493,57 @@ def run_ours(a):
     hi_ = math.inf if hi is None else hi
     scale_p = scale.clone().requires_grad_(True)
     launches = {"n": 0}
+    # launches of OUR kernels per step: forward + backward (+ finalize when it is a separate launch)
+    # (+ AEWGS statistics kernel and its finalize)
+    per_step_launches = ops.launches_per_fwd_bwd(x, scale, zp, lo_, hi_, a.method)
+    keep = {}
 
-    def step():
+    def eager_body():
         xs = x.detach().requires_grad_(True)
         scale_p.grad = None
         y = mhaq_b200.fake_quant(xs, scale_p, zp, lo_, hi_, method=a.method)
         y.backward(go)
-        launches["n"] += 3 + (2 if a.method == "AEWGS" else 0)   # fwd + bwd + finalize (+ AEWGS stats x2)
-        return y, xs.grad, scale_p.grad
+        keep["out"] = (y, xs.grad, scale_p.grad)
+
+    # The step is captured ONCE in a CUDA graph and replayed: with 8 processes on one host the
+    # Python launch path of a 0.8 ms step is exposed to host jitter (round 1: one straggler rank
+    # cost 6.5 % at N=8 in a 16 ms timed window); a replay is one cudaGraphLaunch per step.
+    # The in-kernel noise reads a device-resident Philox state advanced inside the graph, so every
+    # replay draws fresh noise, exactly like the eager step does from torch's generator.
+    graph_note = None
+    graph = None
+    if not a.no_graph_microbench:
+        try:
+            state = torch.tensor([1234 + rank, 0], dtype=torch.int64, device=dev)
+            ops.set_device_philox_state(state)
+
+            def graph_body():
+                ops.reset_philox_call_counter()
+                state[1] += 16
+                eager_body()
+
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    graph_body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            keep.clear()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_body()
+        except Exception as exc:
+            graph, graph_note = None, f"{type(exc).__name__}: {str(exc)[:120]}"
+            ops.set_device_philox_state(None)
+            torch.cuda.synchronize()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            eager_body()
+        launches["n"] += per_step_launches
 
     # clocks / throttle reasons are sampled from before the warm-up to the end of the timed
     # region (nvidia-smi needs ~0.1 s to start; the timed region alone can be shorter than that)
@@ -452,12 +555,17 @@ def run_ours(a):
             if n_warm % 8 == 0:
                 torch.cuda.synchronize()
         launches["n"] = 0                   # gpu_launches counts the timed region only
-        ms = time_region(step, a.steps, use_dist)
+        ranks_ms = []
+        ms = time_region(step, a.steps, use_dist, per_rank=ranks_ms)
     clocks = cs.summary()
     clocks["window"] = f"{n_warm} untimed warm-up steps + the timed region"
     n_l = launches["n"]
     per_step = ms / a.steps
     gbs = world * (BYTES_FWD + BYTES_BWD) * n / (per_step * 1e-3) / 1e9
+    if graph is not None:
+        del graph
+        ops.set_device_philox_state(None)
+    keep.clear()
 
     out = None
     if rank == 0:
@@ -494,16 +602,18 @@ def run_ours(a):
                     "bytes_per_elem": bwd_bytes, "ms_per_launch": round(t_b, 4),
                     "fwd_kernel": {"achieved": round(ach_f, 1), "frac": round(ach_f / peak, 4),
                                    "bytes_per_elem": BYTES_FWD, "ms_per_launch": round(t_f, 4)}}
+        rm = sorted(v / a.steps for v in ranks_ms)
         out = {"metric": METRIC, "value": round(gbs, 1), "unit": "GB/s", "n_gpus": world,
                "steps": a.steps, "warmup": max(a.warmup, 3), "warmup_actual": n_warm,
                "ms_per_step": round(per_step, 4),
+               "per_rank_ms_per_step": {"min": round(rm[0], 4), "median": round(rm[len(rm) // 2], 4),
+                                        "max": round(rm[-1], 4)},
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                "data": "synthetic", "impl": "ours",
-               "config": {"workload": workload_name(a), "elements_per_gpu": n,
-                          "layout": [a.channels, n // a.channels] if a.channels else [n],
-                          "method": a.method, "bits": a.bits, "bytes_per_element": 20,
-                          "l2": "inputs (1 GiB each) far exceed the 126 MB L2; no flush needed",
-                          "multi_gpu": "replicas only (independent tensors per GPU, no data-path collective)"},
+               "config": bench_config(a),
+               "launch": ("step captured once in a CUDA graph and replayed (one cudaGraphLaunch per step; noise from a "
+                          "device-resident Philox state advanced inside the graph)" if graph_note is None and
+                          not a.no_graph_microbench else f"eager Python launches ({graph_note or '--no-graph-microbench'})"),
                "frac_of_hbm_peak": round(gbs / world / peak, 4),
                "roofline": roofline, "clocks": clocks, "gpu_launches": n_l}
 
@@ -529,12 +639,21 @@ def run_ours(a):
             for _ in range(2):
                 e2e_step()
             ms_e = time_region(e2e_step, ke, use_dist) / ke
+            link = host_link_probe(dev, use_dist)
             if rank == 0:
+                by_way = 2 * 4 * n
+                floor_ms = by_way / (link["duplex_each_way_GBps"] * 1e9) * 1e3
                 out["e2e"] = {"value": round(world * 20 * n / (ms_e * 1e-3) / 1e9, 2), "unit": "GB/s",
-                              "h2d_bytes_per_step": 2 * 4 * n, "d2h_bytes_per_step": 2 * 4 * n + 4 * scale.numel(),
+                              "h2d_bytes_per_step": by_way, "d2h_bytes_per_step": by_way + 4 * scale.numel(),
                               "ms_per_step": round(ms_e, 3), "steps": ke,
                               "api": "mhaq_b200.host.fake_quant_fwd_bwd_host: pinned host x/go in, y/gx/g_scale out, "
-                                     "16 row chunks pipelined over full-duplex PCIe (copies inside the timed region)"}
+                                     "16 row chunks pipelined over full-duplex PCIe (copies inside the timed region)",
+                              "host_link": link,
+                              "bound": f"host link, not the GPU: {by_way / 2**30:.0f} GiB each way per step per rank at the measured "
+                                       f"{link['duplex_each_way_GBps']} GB/s each way (all {world} rank(s) copying at once) = "
+                                       f"{floor_ms:.1f} ms of copies vs {ms_e:.1f} ms measured; the kernels need "
+                                       f"{per_step:.2f} ms.  All ranks share one host's DRAM / PCIe root complexes, so the "
+                                       "aggregate does not scale with the GPU count"}
             del hx, hg, hy, hgx
         except Exception as exc:       # e.g. the box refuses 4 GiB of pinned host memory
             if use_dist:
@@ -545,36 +664,41 @@ def run_ours(a):
     x = go = None
     torch.cuda.empty_cache()
     if not a.no_resnet:
-        try:
-            rn = resnet18_leg(a, dev, world, rank, use_dist)
-        except Exception as exc:       # the QAT leg must never take the headline line down with it
-            if use_dist:
-                raise
-            rn = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
-            torch.cuda.empty_cache()
-        if rank == 0:
-            out[qat_key(a)] = rn
+        for spec in qat_specs(a):
+            try:
+                rn = qat_leg(a, dev, world, rank, use_dist, spec, ref_flags=a.ddp_reference_flags)
+            except Exception as exc:       # a QAT leg must never take the headline line down with it
+                if use_dist:
+                    raise
+                rn = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+                torch.cuda.empty_cache()
+            if rank == 0:
+                out[spec["key"]] = rn
+        if use_dist and not a.ddp_reference_flags and not a.qat_model and "resnet18" in a.qat_legs:
+            # the same ResNet-18 step the way the reference's Trainer wraps it (trainer.py:88-97,166)
+            rn = qat_leg(a, dev, world, rank, use_dist, dict(QAT_LEGS["resnet18"]), ref_flags=True)
+            if rank == 0:
+                out["resnet18_w4a4_qat_reference_trainer_flags"] = rn
     if rank == 0:
         if not a.no_eager_ref:
-            out["reference_eager_gpu"] = eager_reference_leg(a, dev)
-            if not a.no_resnet and not use_dist:
-                key = qat_key(a)
-                for cl in ((False, True) if a.channels_last else (False,)):
-                    b = argparse.Namespace(**vars(a))
-                    b.channels_last, b.graph = cl, False
-                    try:
-                        with _EagerReferenceBackend():
-                            rr = resnet18_leg(b, dev, 1, 0, False, profile_share=False)
-                    except Exception as exc:
-                        out["reference_eager_gpu"][key + ("_channels_last" if cl else "")] = {
-                            "error": f"{type(exc).__name__}: {str(exc)[:200]}"}
-                        torch.cuda.empty_cache()
-                        continue
-                    out["reference_eager_gpu"][key + ("_channels_last" if cl else "")] = {
-                        "img_per_s": rr["img_per_s"], "ms_per_step": rr["ms_per_step"],
-                        "what": "same QAT step with every fake-quant routed through the reference's eager "
-                                "ATen chain on this GPU, " + ("channels_last like our leg" if cl else
-                                "row-major NCHW as the reference's Trainer runs it")}
+            # the honest speed-up denominators: the LIVE reference run eagerly on this GPU
+            try:
+                from oracle import ref_bench
+                b = argparse.Namespace(**vars(a))
+                b.log2n = min(a.log2n, 26)
+                out["reference_eager_gpu"] = ref_bench.eager_gpu_microbench(make_inputs(b, dev), a.method, b.log2n)
+                torch.cuda.empty_cache()
+                if not a.no_resnet and not use_dist and any(s["model"] == "resnet18" for s in qat_specs(a)):
+                    B = a.resnet_batch or 256
+                    for cl in ((False, True) if a.channels_last else (False,)):
+                        key = "resnet18_w4a4_qat" + ("_channels_last" if cl else "")
+                        try:
+                            out["reference_eager_gpu"][key] = ref_bench.eager_gpu_resnet18_step(B, cl)
+                        except Exception as exc:
+                            out["reference_eager_gpu"][key] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+                            torch.cuda.empty_cache()
+            except Exception as exc:
+                out["reference_eager_gpu"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
         if not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(a, steps=5, warmup=2)
         if a.sweep:
@@ -588,83 +712,37 @@ def run_ours(a):
 
 # ---------------------------------------------------------------------------
 def cpu_baseline(a, steps, warmup):
-    """The reference's CPU quantizer path (oracle port, same ATen op sequence) on the host cores."""
-    from oracle import fq_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    """The reference's CPU quantizer path on the host cores: the LIVE reference (oracle/_ref)
+    when staged, else the oracle port (`kind` says which)."""
+    from oracle import ref_bench
     log2n = min(a.cpu_log2n, a.log2n)
-    n = 1 << log2n
-    x, go, scale, zp, lo, hi = make_inputs(a, "cpu", log2n)
-    lo_ = -math.inf if lo is None else lo
-    hi_ = math.inf if hi is None else hi
-    sp = scale.clone().requires_grad_(True)
-
-    def step():
-        xs = x.detach().requires_grad_(True)
-        sp.grad = None
-        y = O.fake_quant(xs, sp, zp, lo_, hi_, method=a.method)
-        y.backward(go)
-
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": round(20 * n / dt / 1e9, 3), "unit": "GB/s", "cores": cores, "kind": "port",
-            "ms_per_step": round(dt * 1e3, 2),
-            "sample": f"same workload cut to N=2^{log2n} elements, {warmup} warm-up + {steps} timed steps, "
-                      f"torch {torch.__version__} CPU, {cores} threads"}
-
-
-def cpu_config0_step():
-    """BASELINE configs[0]: ResNet-20 CIFAR-10 GDNSQ(STE) W4A4 QAT step on the CPU, synthetic
-    32x32 batch of 128, through Quantizer(config)().quantize() with every fake-quant routed
-    to the reference's eager ATen chain (oracle port) — the reference's own CPU-runnable case."""
-    from mhaq_b200 import harness
-    torch.manual_seed(0)
-    x = torch.randn(128, 3, 32, 32)
-    t = torch.randint(0, 10, (128,))
-    with _EagerReferenceBackend():
-        q = harness.build_qat("resnet20", "cpu", qnmethod="STE", act_bit=4, weight_bit=4,
-                              distillation=False, num_classes=10, calib_batch=x[:32])
-        opt = q.configure_optimizers()
-        q.train(); q.wrapped_criterion.train()
-        ts = []
-        for i in range(5):
-            t0 = time.perf_counter()
-            loss = q.training_step((x, t), 0)
-            loss.backward()
-            opt.step()
-            opt.zero_grad(set_to_none=True)
-            ts.append(time.perf_counter() - t0)
-    ts = sorted(ts[2:])
-    med = ts[len(ts) // 2]
-    return {"workload": "configs[0] ResNet-20 CIFAR-10 GDNSQ(STE) W4A4 QAT step, batch 128, CPU",
-            "s_per_step": round(med, 3), "img_per_s": round(128 / med, 1),
-            "threads": torch.get_num_threads(), "protocol": "2 warm-up + median of 3"}
+    return ref_bench.cpu_microbench(make_inputs(a, "cpu", log2n), a.method, steps, warmup, log2n, a.log2n)
 
 
 def run_reference(a):
+    """`--impl reference`: the reference's own CPU implementation of the path, all host threads,
+    same metric / config / steps / warm-up as our arm; each step is a bounded sample (N = 2^26 of
+    the workload's 2^28 elements) so the run ends within a few minutes.  This
+    process never imports mhaq_b200 (nothing of the product is loaded)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, a.steps)
-    cb = cpu_baseline(a, steps=min(steps, 10), warmup=max(1, min(a.warmup, 3)))
+    from oracle import ref_bench
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    out = {"metric": METRIC, "value": cb["value"], "unit": "GB/s", "n_gpus": world, "steps": min(steps, 10),
-           "warmup": max(1, min(a.warmup, 3)), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+    cb = cpu_baseline(a, steps=max(1, a.steps), warmup=max(0, a.warmup))
+    out = {"metric": METRIC, "value": cb["value"], "unit": "GB/s", "n_gpus": world, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-           "config": {"workload": workload_name(a), "note": "reference CPU path = oracle port of the "
-                      "reference's ATen op sequence (the Python reference cannot travel to the GPU box)"},
+           "config": bench_config(a),
+           "note": "GB/s is size-normalised (20 B/element x elements / time); see cpu_baseline.sample for the sample",
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
+           "gpu_launches": 0, "product_modules_loaded": sorted(m for m in sys.modules if m.startswith("mhaq_b200"))}
     if not a.no_resnet:
         try:
-            out["cpu_config0_step"] = cpu_config0_step()
+            out["cpu_config0_step"] = ref_bench.config0_step()
         except Exception as exc:   # never let the extra leg break the contract line
-            out["cpu_config0_step"] = {"error": str(exc)[:120]}
+            out["cpu_config0_step"] = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}
     emit(out)
 
 

@@ -13,6 +13,8 @@
  *                              fused with torch's clamp/sub/div/mul/add backward
  *   mhaq_fq_bwd_finalize_f32   the broadcast "sum_to_size" reductions autograd
  *                              performs for scale / zero_point / min_val / max_val
+ *   mhaq_fq_bwd_fused_f32      the two calls above as ONE entry point (and, for per-tensor
+ *                              tensors, ONE kernel: the reduction is finished in-kernel)
  *   mhaq_fq_aewgs_stats_f32    reduce_to_shape(num/e2/me) of QNAEWGS.backward
  *   + _finalize                gdnsq.py:118-124, 150-152 (the caller all-reduces
  *                              the packed [3*n_ch] buffer once, gdnsq.py:126-129)
@@ -22,8 +24,10 @@
  *   mhaq_fq_wrow_fwd_f32 /     the whole per-channel weight path of NoisyConv2d / NoisyLinear.forward
  *   mhaq_fq_wrow_bwd_f32       (gdnsq_conv2d.py:72-98) plus ModelHelper's log2(max-min+2^log_s)
  *                              (utils/model_helper.py:24-25,44) and their autograd, one launch each
- *   mhaq_fq_minmax_finalize    q.aminmax() of NoisyAct.forward (layers/gdnsq_act.py:51-54)
- *                              and the eval-mode asserts (gdnsq.py:211-217)
+ *   mhaq_fq_minmax_finalize    q.aminmax() of NoisyAct.forward (layers/gdnsq_act.py:51-54),
+ *                              the eval-mode asserts (gdnsq.py:211-217) and the input min / max
+ *                              MinMaxObserver takes during calibration
+ *                              (calib/minmaxobserver.py:28-37) — all from the forward's own pass
  *   mhaq_fq_noise_f32          torch.randint_like(input, 2).sub_(0.5)  (gdnsq.py:54)
  *
  * Conventions
@@ -50,7 +54,7 @@
 extern "C" {
 #endif
 
-#define MHAQ_FQ_ABI_VERSION 4
+#define MHAQ_FQ_ABI_VERSION 5
 
 /* gradient estimators — numeric values follow the reference enum
  * QNMethod (src/quantization/gdnsq/gdnsq_utils.py:9-13). */
@@ -70,10 +74,16 @@ extern "C" {
  *              channel, lo = hi = NULL; the finalize returns g_scale = d/d log_wght_s,
  *              g_zp = d/d zero_point.
  * The log modes remove the ~25 tiny elementwise launches autograd otherwise runs per quantizer
- * for exp2 / add / sub and their backward. */
+ * for exp2 / add / sub and their backward.
+ *   UNIT       the value is already scaled — the reference's two-step form
+ *              `v + QN*.apply(v, s)` (gdnsq.py:204-208, `scaled_noise`): s = 1, zero_point = 0, no
+ *              clamp; `scale` (and `zp`, any non-NULL pointer) only fix the channel layout.  The
+ *              finalize returns g_scale = the estimator's own scale gradient (QN*.backward's
+ *              grad_scale: the GDNSQ noise term, gdnsq.py:54-55, or LSQ's, :81-82) and nothing else. */
 #define MHAQ_FQ_PARAMS_LINEAR 0
 #define MHAQ_FQ_PARAMS_ACT_LOG 1
 #define MHAQ_FQ_PARAMS_WEIGHT_LOG 2
+#define MHAQ_FQ_PARAMS_UNIT 3
 
 /* argument errors */
 #define MHAQ_FQ_EINVAL (-1)
@@ -100,19 +110,21 @@ int64_t mhaq_fq_ticket_count(int64_t n_rows, int64_t n_inner, int64_t n_ch);
  * fp32 rounding (no FMA contraction, true division, round-half-even).
  *   y      : fake-quantized output, or NULL
  *   codes  : integer-valued fp32 codes rint(v), or NULL
- *   minmax_ws : NULL, or a workspace (mhaq_fq_workspace_bytes) that receives
- *            per-task {min code, max code, non-finite count} for
- *            mhaq_fq_minmax_finalize (eval mode). */
+ *   minmax_ws : NULL, or a workspace (mhaq_fq_workspace_bytes) that receives per-CTA
+ *            {min code, max code, min input, max input} records for mhaq_fq_minmax_finalize
+ *            (eval mode / calibration; NaN-propagating like torch.aminmax).  The statistics ride
+ *            the same packed fast path as the plain forward (persistent grid, one record per CTA). */
 int mhaq_fq_fwd_f32(const float *x, float *y, float *codes,
                     const float *scale, const float *zp, const float *lo, const float *hi,
                     int scale_stride, int zp_stride, int lo_stride, int hi_stride, int param_mode,
                     int64_t n_rows, int64_t n_inner, int64_t n_ch,
                     double *minmax_ws, void *stream);
 
-/* out[0]=min code, out[1]=max code, out[2]=number of non-finite codes, over
- * the whole tensor. */
+/* out5[0]=min code, out5[1]=max code, out5[2]= 0 if every code is finite else 1 (the eval
+ * asserts of gdnsq.py:211-217 can only fail on non-finite codes), out5[3]=min input,
+ * out5[4]=max input, over the whole tensor. */
 int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_inner,
-                            float *out3, void *stream);
+                            float *out5, void *stream);
 
 /* Backward of the fake-quant op: input gradient plus one fp64 record of partial
  * parameter-gradient sums per task (fp32 per thread -> warp shuffle -> fp64 per CTA).
@@ -136,7 +148,7 @@ int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx,
                     const float *aewgs_stats, double *ws, void *stream);
 
 /* Deterministic second stage, one launch whatever the record count: per-channel sums in
- * a fixed order in fp64 (slices of 1024 records in parallel, then a ticketed last-CTA sum
+ * a fixed order in fp64 (slices of 256 records in parallel, then a ticketed last-CTA sum
  * of the slice sums in index order; no floating-point atomics, bitwise reproducible).
  * Each output is [n_ch] floats (or NULL to skip):
  *   g_scale = d/d scale,  g_zp = d/d zero_point,  g_lo = d/d min_val,  g_hi = d/d max_val. */
@@ -147,6 +159,25 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets,
                              int64_t n_rows, int64_t n_inner, int64_t n_ch,
                              float *g_scale, float *g_zp, float *g_lo, float *g_hi,
                              void *stream);
+
+/* mhaq_fq_bwd_f32 + mhaq_fq_bwd_finalize_f32 as one entry point (same arguments, the union of
+ * the two lists).  For a per-tensor tensor (n_rows = n_ch = 1: every activation) with the
+ * STE / LSQ estimator, gradient w.r.t. y and at most 2^26 elements it is ONE kernel: a
+ * persistent, balanced grid (<= SMs x 5 blocks, each block one contiguous range) whose last
+ * block to finish (ticket) sums the per-block fp64 records in index order and writes the
+ * gradients — no second launch, no per-task flushes; bitwise reproducible on a given device.
+ * Everything else runs the two launches above.  mhaq_fq_bwd_single_launch() tells which (for
+ * 16-byte aligned operands). */
+int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx,
+                          const float *scale, const float *zp, const float *lo, const float *hi,
+                          int scale_stride, int zp_stride, int lo_stride, int hi_stride, int param_mode,
+                          int64_t n_rows, int64_t n_inner, int64_t n_ch,
+                          int method, int go_is_code_grad,
+                          const float *r, uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                          const float *aewgs_stats, double *ws, unsigned int *tickets,
+                          float *g_scale, float *g_zp, float *g_lo, float *g_hi, void *stream);
+int mhaq_fq_bwd_single_launch(int64_t n_rows, int64_t n_inner, int64_t n_ch, int method,
+                              int go_is_code_grad);
 
 /* AEWGS statistics: per-channel sums of sign(g)*e, e*e, e  (e = rint(v)-v). */
 int mhaq_fq_aewgs_stats_f32(const float *go, const float *x,

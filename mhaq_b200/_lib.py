@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MHAQ_FQ_LIB: experiment knob to load an alternative build of the same ABI
 LIB_PATH = os.environ.get("MHAQ_FQ_LIB") or os.path.join(_HERE, "csrc", "libmhaq_fq.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 NPART = 8  # MHAQ_FQ_NPART
 
 # name -> (restype, argtypes); mirrors include/mhaq_fq.h one to one
@@ -33,6 +33,10 @@ _SIGNATURES = {
                                 _P, _P, _P, _P]),
     "mhaq_fq_bwd_finalize_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                          c_int64, c_int64, c_int64, _P, _P, _P, _P, _P]),
+    "mhaq_fq_bwd_fused_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                      c_int64, c_int64, c_int64, c_int, c_int, _P, c_uint64, c_uint64,
+                                      _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mhaq_fq_bwd_single_launch": (c_int, [c_int64, c_int64, c_int64, c_int, c_int]),
     "mhaq_fq_aewgs_stats_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                         c_int64, c_int64, c_int64, c_int, _P, _P]),
     "mhaq_fq_aewgs_stats_finalize_f32": (c_int, [_P, c_int64, c_int64, c_int64, _P, _P]),

@@ -23,3 +23,28 @@ MType = _enum("MType", {**_VISION_TASKS, "LM": 10})
 QScheme = _enum("QScheme", {"PER_TENSOR": 0, "PER_CHANNEL": 1})
 #: quantization algorithm family
 QMethod = _enum("QMethod", {"GDNSQ": 0})
+
+
+def scheme_id(qscheme) -> int:
+    """0 = per tensor, 1 = per channel, from this package's ``QScheme``, the integer a YAML config
+    carries, the member name, or ANOTHER package's enum with the same contract — the reference's
+    own ``src.aux.types.QScheme`` when its ``GDNSQQuant`` constructs this repo's layer classes
+    (INTEGRATION.md §B).  Stored attributes are kept as given; comparisons go through here."""
+    if isinstance(qscheme, QScheme):
+        return qscheme.value
+    if isinstance(qscheme, Enum):
+        name, value = qscheme.name, qscheme.value
+        if name in QScheme.__members__ and QScheme[name].value == value:
+            return value
+        raise ValueError(f"unknown quantization scheme {qscheme!r}")
+    if isinstance(qscheme, str):
+        return QScheme[qscheme].value
+    return QScheme(int(qscheme)).value
+
+
+def is_per_channel(qscheme) -> bool:
+    return scheme_id(qscheme) == QScheme.PER_CHANNEL.value
+
+
+def is_per_tensor(qscheme) -> bool:
+    return scheme_id(qscheme) == QScheme.PER_TENSOR.value

@@ -85,7 +85,10 @@ __host__ __device__ inline Geom make_geom(int64_t n_rows, int64_t n_inner, int64
 //            s = exp2(log_wght_s)                               (gdnsq_conv2d.py:72, 80-84)
 // exp2f is the same libdevice routine torch's CUDA exp2 kernel calls, so the scale has the
 // same bits as torch.exp2(log_s) (checked by tests/test_gpu_layers.py).
-enum { PARAMS_LINEAR = 0, PARAMS_ACT_LOG = 1, PARAMS_WEIGHT_LOG = 2 };
+//   UNIT   : the value is ALREADY scaled (the reference's two-step form `v + QN*.apply(v, s)`,
+//            gdnsq.py:204-208): s = 1, zp = 0, no clamp; `scale` only fixes the channel layout.
+//            The finalize returns the estimator's own scale gradient (the noise / LSQ term).
+enum { PARAMS_LINEAR = 0, PARAMS_ACT_LOG = 1, PARAMS_WEIGHT_LOG = 2, PARAMS_UNIT = 3 };
 
 struct QParams {
     const float *scale, *zp, *lo, *hi;
@@ -106,6 +109,10 @@ __device__ __forceinline__ QConst load_qconst(const QParams &p, int64_t ch) {
         q.zp = b;
         q.lo = b;
         q.hi = __fsub_rn(__fadd_rn(b, exp2f(__ldg(p.lo))), q.s);      // (act_b + q) - s
+        return q;
+    }
+    if (p.mode == PARAMS_UNIT) {
+        q.s = 1.f; q.zp = 0.f; q.lo = -INFINITY; q.hi = INFINITY;
         return q;
     }
     const float sv = __ldg(p.scale + ch * p.ss);

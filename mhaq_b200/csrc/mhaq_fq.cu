@@ -34,10 +34,39 @@ enum { NOISE_PHILOX = 0, NOISE_EXPLICIT = 1, NOISE_NONE = 2 };
 // ===========================================================================
 // Forward
 // ===========================================================================
+// Eval-mode statistics (STATS): min / max CODE (NoisyAct.bw, gdnsq_act.py:51-54; the eval asserts
+// of gdnsq.py:211-217 reduce to "every code finite") and min / max INPUT (what MinMaxObserver
+// takes from the same tensor during calibration, calib/minmaxobserver.py:28-37) in the same pass.
+// NaN-propagating min / max, like torch.min / torch.max / aminmax.
 struct FwdStat {
-    float cmin, cmax;
-    unsigned bad;
+    float cmin, cmax, xmin, xmax;
 };
+__device__ __forceinline__ float min_nan(float a, float b) {
+    float d;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+__device__ __forceinline__ void stat_push(FwdStat &st, float x, float c) {
+    st.cmin = min_nan(st.cmin, c);
+    st.cmax = max_nan(st.cmax, c);
+    st.xmin = min_nan(st.xmin, x);
+    st.xmax = max_nan(st.xmax, x);
+}
+__device__ __forceinline__ float warp_min_nan(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min_nan(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max_nan(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max_nan(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
 
 // General path: true IEEE division, any operand (also the ragged / unaligned tiles).
 __device__ __forceinline__ float fwd_elem(float x, const QConst &q, float &code) {
@@ -73,22 +102,27 @@ __device__ __forceinline__ float absmax4(float m, const float4 &v) {
     return fmaxf(fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
 }
 
-template <bool VEC, bool CLAMP>
+// STATS = false: one CTA per task (grid = n_tasks), no statistics — the training forward.
+// STATS = true : persistent (grid <= kEvalGridCap), every CTA walks tasks blockIdx.x, +gridDim.x, ...
+//                keeps its running min / max in registers (min / max are exact and order-free, so
+//                the assignment of tasks to CTAs does not matter) and writes ONE record at the end.
+constexpr int kEvalGridCap = 148 * 8;
+
+template <bool VEC, bool CLAMP, bool STATS>
 __global__ void __launch_bounds__(kThreads)
 fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restrict__ codes,
               QParams prm, Geom g, double *__restrict__ mm_ws) {
     const int tid = threadIdx.x;
-    __shared__ float s_red[3][kThreads / 32];
+    FwdStat st = {INFINITY, -INFINITY, INFINITY, -INFINITY};
     for (int64_t t = blockIdx.x; t < g.n_tasks; t += gridDim.x) {
         const Task k = make_task(g, t);
         const QConst q = load_qconst(prm, k.ch);
         const Div2 dv = make_div2(q.s, __frcp_rn(q.s));
         const f32x2 zpn = bc2(-q.zp), zp2 = bc2(q.zp);
-        const bool fast_ok = VEC && scale_fast_ok(q.s) && (mm_ws == nullptr);
+        const bool fast_ok = VEC && scale_fast_ok(q.s);
         const float *xr = x + k.row_off;
         float *yr = y ? y + k.row_off : nullptr;
         float *cr = codes ? codes + k.row_off : nullptr;
-        FwdStat st = {INFINITY, -INFINITY, 0u};
         for (int64_t sub = k.q0; sub < k.q1; ++sub) {
             const int64_t base = sub * kSubElems + tid * 4;
             const bool full = (sub + 1) * kSubElems <= g.n_inner;
@@ -119,11 +153,17 @@ fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restr
                         const int64_t p = base + (b * kU + u) * kIterElems;
                         if (yr) st_stream4(yr + p, yv);
                         if (cr) st_stream4(cr + p, cv);
+                        if (STATS) {
+                            stat_push(st, xv[u].x, cv.x);
+                            stat_push(st, xv[u].y, cv.y);
+                            stat_push(st, xv[u].z, cv.z);
+                            stat_push(st, xv[u].w, cv.w);
+                        }
                     }
                 }
                 continue;
             }
-            // ---------------- general path: ragged / unaligned / eval statistics ----------------
+            // ---------------- general path: ragged / unaligned / out-of-range scale ----------------
 #pragma unroll 1
             for (int b = 0; b < kSubIters / kU; ++b) {
                 float4 xv[kU];
@@ -145,71 +185,68 @@ fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restr
                     yv.w = fwd_elem(xv[u].w, q, cv.w);
                     if (yr) store4<VEC>(yr, p, g.n_inner, yv);
                     if (cr) store4<VEC>(cr, p, g.n_inner, cv);
-                    if (mm_ws) {
+                    if (STATS) {
                         const float ce[4] = {cv.x, cv.y, cv.z, cv.w};
+                        const float xe[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (e < nv[u]) {
-                                st.cmin = fminf(st.cmin, ce[e]);
-                                st.cmax = fmaxf(st.cmax, ce[e]);
-                                st.bad += !(fabsf(ce[e]) < INFINITY);
-                            }
-                        }
+                        for (int e = 0; e < 4; ++e)
+                            if (e < nv[u]) stat_push(st, xe[e], ce[e]);
                     }
                 }
             }
         }
-        if (mm_ws) {
-            float mn = warp_min(st.cmin), mx = warp_max(st.cmax);
-            float bd = warp_sum((float)st.bad);
-            if ((tid & 31) == 0) {
-                s_red[0][tid >> 5] = mn;
-                s_red[1][tid >> 5] = mx;
-                s_red[2][tid >> 5] = bd;
+    }
+    if (STATS) {
+        __shared__ float s_red[4][kThreads / 32];
+        const float a = warp_min_nan(st.cmin), b = warp_max_nan(st.cmax);
+        const float c = warp_min_nan(st.xmin), d = warp_max_nan(st.xmax);
+        if ((tid & 31) == 0) {
+            s_red[0][tid >> 5] = a; s_red[1][tid >> 5] = b;
+            s_red[2][tid >> 5] = c; s_red[3][tid >> 5] = d;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float r0 = s_red[0][0], r1 = s_red[1][0], r2 = s_red[2][0], r3 = s_red[3][0];
+            for (int w = 1; w < kThreads / 32; ++w) {
+                r0 = min_nan(r0, s_red[0][w]); r1 = max_nan(r1, s_red[1][w]);
+                r2 = min_nan(r2, s_red[2][w]); r3 = max_nan(r3, s_red[3][w]);
             }
-            __syncthreads();
-            if (tid == 0) {
-                float a = s_red[0][0], b = s_red[1][0], c = s_red[2][0];
-                for (int w = 1; w < kThreads / 32; ++w) {
-                    a = fminf(a, s_red[0][w]);
-                    b = fmaxf(b, s_red[1][w]);
-                    c += s_red[2][w];
-                }
-                double *rec = mm_ws + t * kNPart;
-                rec[0] = a;
-                rec[1] = b;
-                rec[2] = c;
-            }
-            __syncthreads();
+            float *rec = reinterpret_cast<float *>(mm_ws + (int64_t)blockIdx.x * kNPart);
+            rec[0] = r0; rec[1] = r1; rec[2] = r2; rec[3] = r3;
         }
     }
 }
 
+// out5 = {min code, max code, non-finite flag, min input, max input} from the per-CTA records
 __global__ void __launch_bounds__(256)
-fq_minmax_finalize_kernel(const double *__restrict__ ws, int64_t n_tasks, float *__restrict__ out3) {
-    __shared__ double s[3][256];
-    double mn = INFINITY, mx = -INFINITY, bad = 0.0;
-    for (int64_t t = threadIdx.x; t < n_tasks; t += 256) {
-        mn = fmin(mn, ws[t * kNPart + 0]);
-        mx = fmax(mx, ws[t * kNPart + 1]);
-        bad += ws[t * kNPart + 2];
+fq_minmax_finalize_kernel(const double *__restrict__ ws, int64_t n_rec, float *__restrict__ out5) {
+    __shared__ float s[4][256];
+    float v[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+    for (int64_t t = threadIdx.x; t < n_rec; t += 256) {
+        const float *rec = reinterpret_cast<const float *>(ws + t * kNPart);
+        v[0] = min_nan(v[0], rec[0]); v[1] = max_nan(v[1], rec[1]);
+        v[2] = min_nan(v[2], rec[2]); v[3] = max_nan(v[3], rec[3]);
     }
-    s[0][threadIdx.x] = mn;
-    s[1][threadIdx.x] = mx;
-    s[2][threadIdx.x] = bad;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) s[m][threadIdx.x] = v[m];
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) {
-            s[0][threadIdx.x] = fmin(s[0][threadIdx.x], s[0][threadIdx.x + o]);
-            s[1][threadIdx.x] = fmax(s[1][threadIdx.x], s[1][threadIdx.x + o]);
-            s[2][threadIdx.x] += s[2][threadIdx.x + o];
+            s[0][threadIdx.x] = min_nan(s[0][threadIdx.x], s[0][threadIdx.x + o]);
+            s[1][threadIdx.x] = max_nan(s[1][threadIdx.x], s[1][threadIdx.x + o]);
+            s[2][threadIdx.x] = min_nan(s[2][threadIdx.x], s[2][threadIdx.x + o]);
+            s[3][threadIdx.x] = max_nan(s[3][threadIdx.x], s[3][threadIdx.x + o]);
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        out3[0] = (float)s[0][0];
-        out3[1] = (float)s[1][0];
-        out3[2] = (float)s[2][0];
+        const float cmin = s[0][0], cmax = s[1][0];
+        out5[0] = cmin;
+        out5[1] = cmax;
+        // every code is finite  <=>  both extremes are (NaN propagates into both)
+        out5[2] = (fabsf(cmin) < INFINITY && fabsf(cmax) < INFINITY) ? 0.f : 1.f;
+        out5[3] = s[2][0];
+        out5[4] = s[3][0];
     }
 }
 
@@ -489,12 +526,14 @@ __device__ __forceinline__ int64_t chan_record(const Geom &g, int64_t ch, int64_
 
 template <int NCOL, typename Emit>
 __device__ __forceinline__ void finalize_channel(const double *ws, double *slice_ws,
-                                                 unsigned int *tickets, const Geom &g, Emit emit) {
+                                                 unsigned int *tickets, const Geom &g, int64_t n_sl,
+                                                 Emit emit) {
     __shared__ double s[NCOL][kFinThreads / 32];
     __shared__ int s_last;
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;
-    const int64_t ch = blockIdx.y, sl = blockIdx.x, n_sl = gridDim.x;
+    // 1-D grid of n_ch * n_sl CTAs (the channel count is not limited by gridDim.y)
+    const int64_t ch = (int64_t)blockIdx.x / n_sl, sl = (int64_t)blockIdx.x - ch * n_sl;
     const int64_t recs = (g.n_rows / g.n_ch) * g.tasks_per_row;
     const int64_t i0 = sl * kSliceRecs;
     const int64_t i1 = (i0 + kSliceRecs < recs) ? i0 + kSliceRecs : recs;
@@ -541,30 +580,39 @@ __device__ __forceinline__ void finalize_channel(const double *ws, double *slice
 //               o1 = d/d act_b     = S_zp + S_lo + S_hi           (zp, lo and hi all contain act_b)
 //               o2 = d/d log_act_q = S_hi * q * ln2
 //   WEIGHT_LOG: o0 = d/d log_wght_s = d/ds * s * ln2,  o1 = d/d zero_point
+//   UNIT      : o0 = S_noise alone: the estimator's own scale gradient (QN*.backward's grad_scale,
+//               gdnsq.py:54-55, 81-82) — the unit divisor is not a parameter
 // i.e. the Exp2Backward / AddBackward / SubBackward nodes autograd would run on the tiny
 // parameter tensors (gdnsq_act.py:42-48), folded into the last thread of the reduction.
+__device__ __forceinline__ void emit_param_grads(const QParams &prm, int64_t ch, const double (&a)[5],
+                                                 float *o0, float *o1, float *o2, float *o3) {
+    const double ds = a[0] + a[1];
+    constexpr double kLn2 = 0.693147180559945309417;
+    if (prm.mode == PARAMS_ACT_LOG) {
+        const double s = (double)exp2f(prm.scale[0]), q = (double)exp2f(prm.lo[0]);
+        if (o0) o0[0] = (float)((ds - a[4]) * s * kLn2);
+        if (o1) o1[0] = (float)(a[2] + a[3] + a[4]);
+        if (o2) o2[0] = (float)(a[4] * q * kLn2);
+    } else if (prm.mode == PARAMS_WEIGHT_LOG) {
+        const double s = (double)exp2f(prm.scale[ch * prm.ss]);
+        if (o0) o0[ch] = (float)(ds * s * kLn2);
+        if (o1) o1[ch] = (float)a[2];
+    } else if (prm.mode == PARAMS_UNIT) {
+        if (o0) o0[ch] = (float)a[1];
+    } else {
+        if (o0) o0[ch] = (float)ds;
+        if (o1) o1[ch] = (float)a[2];
+        if (o2) o2[ch] = (float)a[3];
+        if (o3) o3[ch] = (float)a[4];
+    }
+}
+
 __global__ void __launch_bounds__(kFinThreads)
 fq_bwd_finalize_kernel(const double *__restrict__ ws, double *slice_ws, unsigned int *tickets,
-                       Geom g, QParams prm, float *__restrict__ o0, float *__restrict__ o1,
-                       float *__restrict__ o2, float *__restrict__ o3) {
-    finalize_channel<5>(ws, slice_ws, tickets, g, [=](int64_t ch, const double (&a)[5]) {
-        const double ds = a[0] + a[1];
-        constexpr double kLn2 = 0.693147180559945309417;
-        if (prm.mode == PARAMS_ACT_LOG) {
-            const double s = (double)exp2f(prm.scale[0]), q = (double)exp2f(prm.lo[0]);
-            if (o0) o0[0] = (float)((ds - a[4]) * s * kLn2);
-            if (o1) o1[0] = (float)(a[2] + a[3] + a[4]);
-            if (o2) o2[0] = (float)(a[4] * q * kLn2);
-        } else if (prm.mode == PARAMS_WEIGHT_LOG) {
-            const double s = (double)exp2f(prm.scale[ch * prm.ss]);
-            if (o0) o0[ch] = (float)(ds * s * kLn2);
-            if (o1) o1[ch] = (float)a[2];
-        } else {
-            if (o0) o0[ch] = (float)ds;
-            if (o1) o1[ch] = (float)a[2];
-            if (o2) o2[ch] = (float)a[3];
-            if (o3) o3[ch] = (float)a[4];
-        }
+                       Geom g, int64_t n_sl, QParams prm, float *__restrict__ o0,
+                       float *__restrict__ o1, float *__restrict__ o2, float *__restrict__ o3) {
+    finalize_channel<5>(ws, slice_ws, tickets, g, n_sl, [=](int64_t ch, const double (&a)[5]) {
+        emit_param_grads(prm, ch, a, o0, o1, o2, o3);
     });
 }
 
@@ -714,6 +762,208 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
             upk2(a2.sz, l, h); acc.sz += l + h;
         }
         flush_record<CLAMP>(acc, t, ws);
+    }
+}
+
+// ===========================================================================
+// Flat (per-tensor) backward: persistent, balanced, reduction finished in-kernel
+// ===========================================================================
+// Activation tensors of real models are per-tensor and mid-sized (1-50 M elements): a few waves of
+// CTAs, where a second (finalize) launch and per-task flushes are a visible fraction of the
+// kernel.  This variant is launched with at most `cap` = SMs x resident-CTAs blocks; block b owns
+// the contiguous range of `per_cta` 2048-element batches [b*per_cta, ...) — every block resident at
+// once with (almost) the same amount of work, no waves — folds its fp32 per-thread partials into
+// per-warp fp64 accumulators every 4 batches (64 elements per thread, like a 2-sub-tile task of
+// the streaming kernel), writes ONE record, and the last block to finish (ticket) sums the
+// <= cap records in index order and applies emit_param_grads.  Deterministic: the partition and
+// both summation orders are functions of the shape only; the ticket decides who sums, not how.
+// The noise stream is the streaming kernel's (a function of the element position only).
+// The release fence that made an in-kernel reduction unattractive per 8 Ki-element task
+//  is paid once per CTA lifetime here.
+constexpr int kBatchElems = kIterElems * kU;      // 2048
+constexpr int kFlatGroup = 4;                     // batches between fp32 -> fp64 folds
+constexpr int kFlatCapMax = 2048;                 // upper bound on the grid (workspace sizing)
+
+struct FlatGeom {
+    int64_t n;         // elements
+    int64_t full;      // full batches
+    int64_t per_cta;   // batches per block
+    int grid;          // blocks == records
+};
+__host__ __device__ inline FlatGeom make_flat_geom(int64_t n, int cap) {
+    FlatGeom f;
+    f.n = n;
+    f.full = n / kBatchElems;
+    if (cap > kFlatCapMax) cap = kFlatCapMax;
+    if (cap < 1) cap = 1;
+    int64_t k = (f.full + cap - 1) / cap;
+    if (k < 1) k = 1;
+    f.per_cta = k;
+    int64_t gsz = (f.full + k - 1) / k;
+    if (gsz < 1) gsz = 1;
+    f.grid = (int)gsz;
+    return f;
+}
+
+template <bool CLAMP>
+__device__ __forceinline__ void flat_fold(Acc &acc, Acc2 &a2, double (*s_acc)[kThreads / 32]) {
+    float l, h;
+    upk2(a2.se, l, h); acc.se += l + h;
+    upk2(a2.sn, l, h); acc.sn -= l + h;          // accumulated with the opposite sign
+    upk2(a2.sz, l, h); acc.sz += l + h;
+    const float v0 = warp_sum(acc.se), v1 = warp_sum(acc.sn), v2 = warp_sum(acc.sz);
+    const float v3 = CLAMP ? warp_sum(acc.sl) : 0.f, v4 = CLAMP ? warp_sum(acc.sh) : 0.f;
+    if ((threadIdx.x & 31) == 0) {               // each warp owns its slot: no barrier needed
+        const int w = threadIdx.x >> 5;
+        s_acc[0][w] += (double)v0; s_acc[1][w] += (double)v1; s_acc[2][w] += (double)v2;
+        if (CLAMP) { s_acc[3][w] += (double)v3; s_acc[4][w] += (double)v4; }
+    }
+    acc = {0.f, 0.f, 0.f, 0.f, 0.f};
+    a2 = {0ull, 0ull, 0ull};
+}
+
+template <int METHOD, bool CLAMP, int NOISE>
+__global__ void __launch_bounds__(kThreads, MHAQ_BWD_MIN_CTAS)
+fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, float *__restrict__ gx,
+                   QParams prm, FlatGeom f, const float *__restrict__ r, uint64_t seed,
+                   uint64_t offset, const uint64_t *__restrict__ philox_dev, double *__restrict__ ws,
+                   unsigned int *ticket, float *__restrict__ o0, float *__restrict__ o1,
+                   float *__restrict__ o2, float *__restrict__ o3) {
+    static_assert(METHOD == MHAQ_FQ_STE || METHOD == MHAQ_FQ_LSQ, "flat backward: STE / LSQ only");
+    const int tid = threadIdx.x;
+    __shared__ double s_acc[5][kThreads / 32];
+    __shared__ double s_fin[5][kFinThreads / 32];
+    __shared__ int s_last;
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int m = 0; m < 5; ++m) s_acc[m][tid >> 5] = 0.0;
+    }
+    PhiloxKey key = {0, 0, 0, 0};
+    if (NOISE == NOISE_PHILOX) key = make_key(seed, offset, philox_dev);
+    const int64_t supers_per_row = (f.n + kSuperElems - 1) / kSuperElems;
+    const QConst q = load_qconst(prm, 0);
+    BwdConst bc;
+    bc.smul = q.s;
+    bc.rcp = __frcp_rn(q.s);
+    bc.lo_lt_hi = q.lo < q.hi;
+    bc.lo_gt_hi = q.lo > q.hi;
+    bc.delta = 0.f;
+    const bool fast_ok = scale_fast_ok(q.s) && (!CLAMP || bc.lo_lt_hi);
+    PairConst pc;
+    pc.d = make_div2(q.s, bc.rcp);
+    pc.zpn = bc2(-q.zp);
+    pc.c = bc2(kInvSqrt3);
+    pc.half = bc2(0.5f);
+    Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f};
+    Acc2 a2 = {0ull, 0ull, 0ull};
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    int64_t curT = -1;
+    int in_group = 0;
+
+    const int64_t b0 = (int64_t)blockIdx.x * f.per_cta;
+    int64_t b1 = b0 + f.per_cta;
+    if (b1 > f.full) b1 = f.full;
+    // the ragged tail (< one batch) belongs to the last block
+    const bool tail = (blockIdx.x == gridDim.x - 1) && (f.full * kBatchElems < f.n);
+    const int64_t b_end = tail ? f.full + 1 : b1;
+
+    for (int64_t B = b0; B < b_end; ++B) {
+        const bool is_tail = B >= b1;                        // only possible for the last block
+        const int64_t Bq = is_tail ? f.full : B;
+        const int64_t base = Bq * kBatchElems + tid * 4;
+        const int it0 = (int)(Bq & 7) * kU;                  // iteration index inside the super-tile
+        if (NOISE == NOISE_PHILOX) {
+            const int64_t T = Bq >> 3;                       // 8 batches per 16384-element super-tile
+            if (T != curT) {
+                rnd = noise_block(key, 0, supers_per_row, T, tid);
+                curT = T;
+            }
+        }
+        if (fast_ok && !is_tail) {
+            uint32_t nw = 0;
+            if (NOISE == NOISE_PHILOX) {
+                const int wi = it0 >> 3;                     // 32-bit word of the 128-bit block
+                nw = ~((wi < 2) ? ((wi == 0) ? rnd.x : rnd.y) : ((wi == 2) ? rnd.z : rnd.w));
+                if (it0 & 4) nw >>= 16;                      // second half of the word's 8 iterations
+            }
+            float4 xv[kU], gv[kU], rv4[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int64_t p = base + u * kIterElems;
+                xv[u] = ld_stream4(x + p);
+                gv[u] = ld_stream4(go + p);
+                rv4[u] = (NOISE == NOISE_EXPLICIT) ? ld_stream4(r + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            uint32_t mn = 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) mn = nzmin4(mn, gv[u]);
+            const bool odd = mn < kGoLoBits2m1;
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int64_t p = base + u * kIterElems;
+                constexpr int kTop = 31;
+                const int sh = u * 4;
+                float4 o;
+                bwd_pair_fast<METHOD, CLAMP, NOISE>(xv[u].x, xv[u].y, gv[u].x, gv[u].y, rv4[u].x, rv4[u].y,
+                                                    nw << (kTop - sh - 0), nw << (kTop - sh - 1), q, pc, a2, acc, o.x, o.y);
+                bwd_pair_fast<METHOD, CLAMP, NOISE>(xv[u].z, xv[u].w, gv[u].z, gv[u].w, rv4[u].z, rv4[u].w,
+                                                    nw << (kTop - sh - 2), nw << (kTop - sh - 3), q, pc, a2, acc, o.z, o.w);
+                if (gx) st_stream4(gx + p, o);
+            }
+            if (odd && gx)   // rare: exact IEEE division for the input gradient
+                fix_batch_exact<METHOD, CLAMP>(x, go, gx, base, q, bc.smul, bc.delta);
+        } else {
+            // general path: true IEEE division (out-of-range scale, lo >= hi) and the ragged tail
+#pragma unroll 1
+            for (int u = 0; u < kU; ++u) {
+                const int64_t p = base + (int64_t)u * kIterElems;
+                const int nv = is_tail ? valid4<true>(p, f.n) : 4;
+                if (!nv) continue;
+                const float4 xe = ld_stream4(x + p), ge = ld_stream4(go + p);
+                float4 re = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (NOISE == NOISE_EXPLICIT) re = ld_stream4(r + p);
+                uint32_t inv = 0;
+                if (NOISE == NOISE_PHILOX) inv = ~noise_nibble(rnd, it0 + u);
+                float4 o;
+                o.x = bwd_elem<METHOD, CLAMP, NOISE, false, false>(xe.x, ge.x, re.x, inv << 31, q, bc, acc);
+                o.y = bwd_elem<METHOD, CLAMP, NOISE, false, false>(xe.y, ge.y, re.y, inv << 30, q, bc, acc);
+                o.z = bwd_elem<METHOD, CLAMP, NOISE, false, false>(xe.z, ge.z, re.z, inv << 29, q, bc, acc);
+                o.w = bwd_elem<METHOD, CLAMP, NOISE, false, false>(xe.w, ge.w, re.w, inv << 28, q, bc, acc);
+                if (gx) st_stream4(gx + p, o);
+            }
+        }
+        if (++in_group == kFlatGroup) {
+            flat_fold<CLAMP>(acc, a2, s_acc);
+            in_group = 0;
+        }
+    }
+    if (in_group) flat_fold<CLAMP>(acc, a2, s_acc);
+    __syncthreads();
+    if (tid == 0) {
+        double *rec = ws + (int64_t)blockIdx.x * kNPart;
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {
+            double a = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) a += s_acc[m][w];
+            rec[m] = a;
+        }
+        __threadfence();                                     // record visible before the ticket
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = tid; i < (int)gridDim.x; i += kThreads) {
+        const double *rec = ws + (int64_t)i * kNPart;
+#pragma unroll
+        for (int m = 0; m < 5; ++m) a[m] += __ldcg(rec + m);
+    }
+    block_sum_cols<5>(a, s_fin);
+    if (tid == 0) {
+        emit_param_grads(prm, 0, a, o0, o1, o2, o3);
+        *ticket = 0u;
     }
 }
 
@@ -971,7 +1221,7 @@ inline int check_common(const void *x, const float *scale, const float *zp, int6
     return 0;
 }
 inline bool stride_ok(int s) { return s == 0 || s == 1; }
-inline bool mode_ok(int m) { return m >= PARAMS_LINEAR && m <= PARAMS_WEIGHT_LOG; }
+inline bool mode_ok(int m) { return m >= PARAMS_LINEAR && m <= PARAMS_UNIT; }
 // ACT_LOG needs all of log_act_s (scale), act_b (zp) and log_act_q (lo) and is per-tensor
 inline int check_mode(int mode, const float *lo, int64_t n_ch) {
     if (!mode_ok(mode)) return MHAQ_FQ_EINVAL;
@@ -1004,6 +1254,10 @@ inline Geom stream_geom(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
 inline Geom reduce_geom(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
     static const int ov = env_int("MHAQ_FQ_BWD_SPT");
     return make_geom(n_rows, n_inner, n_ch, GEOM_REDUCE, ov);
+}
+
+inline int eval_grid(int64_t n_tasks) {
+    return (int)(n_tasks < kEvalGridCap ? n_tasks : kEvalGridCap);
 }
 
 inline int last_error() {
@@ -1055,6 +1309,52 @@ int launch_wrow_bwd(bool vec, int grid, cudaStream_t st, const float *go, const 
     return last_error();
 }
 
+// blocks the flat backward may use: SMs x resident CTAs (MHAQ_FQ_FLAT_CTAS_PER_SM overrides the
+// per-SM factor for experiments)
+inline int flat_cap() {
+    static int cap = 0;
+    if (cap == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+        const int per_sm = env_int("MHAQ_FQ_FLAT_CTAS_PER_SM");
+        cap = sms * (per_sm > 0 ? per_sm : MHAQ_BWD_MIN_CTAS);
+    }
+    return cap;
+}
+// Largest tensor (elements) the flat backward takes; above it the dynamic one-CTA-per-task
+// streaming kernel + finalize launch wins (the hardware scheduler balances a long tail better than
+// a static partition).  MHAQ_FQ_FLAT_MAX_LOG2 overrides (0 disables the flat kernel).
+inline int64_t flat_max_elems() {
+    static int64_t mx = -1;
+    if (mx < 0) {
+        const char *e = getenv("MHAQ_FQ_FLAT_MAX_LOG2");
+        const int l2 = e ? atoi(e) : 26;
+        mx = l2 <= 0 ? 0 : (int64_t)1 << l2;
+    }
+    return mx;
+}
+inline bool flat_shape_ok(int64_t n_rows, int64_t n_inner, int64_t n_ch, int method, int codegrad) {
+    return n_rows == 1 && n_ch == 1 && !codegrad && (n_inner % 4 == 0) && n_inner <= flat_max_elems() &&
+           (method == MHAQ_FQ_STE || method == MHAQ_FQ_LSQ);
+}
+
+template <int METHOD, bool CLAMP>
+int launch_bwd_flat(bool explicit_r, const FlatGeom &f, cudaStream_t st, const float *go, const float *x,
+                    float *gx, const QParams &prm, const float *r, uint64_t seed, uint64_t offset,
+                    const uint64_t *philox_dev, double *ws, unsigned int *ticket, float *o0, float *o1,
+                    float *o2, float *o3) {
+#define MHAQ_FLAT(N)                                                                              \
+    fq_bwd_flat_kernel<METHOD, CLAMP, N><<<f.grid, kThreads, 0, st>>>(                            \
+        go, x, gx, prm, f, r, seed, offset, philox_dev, ws, ticket, o0, o1, o2, o3)
+    if (METHOD == MHAQ_FQ_LSQ) MHAQ_FLAT(NOISE_NONE);
+    else if (explicit_r) MHAQ_FLAT(NOISE_EXPLICIT);
+    else MHAQ_FLAT(NOISE_PHILOX);
+#undef MHAQ_FLAT
+    return last_error();
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -1079,12 +1379,13 @@ static inline int64_t n_slices_of(const Geom &g) {
 }
 
 int64_t mhaq_fq_workspace_bytes(int64_t n_rows, int64_t n_inner) {
-    if (n_rows <= 0 || n_inner <= 0) return kNPart * (int64_t)sizeof(double);
+    if (n_rows <= 0 || n_inner <= 0) return (1 + kFlatCapMax) * kNPart * (int64_t)sizeof(double);
     const Geom gs = stream_geom(n_rows, n_inner, 1), gr = reduce_geom(n_rows, n_inner, 1);
     const int64_t tasks = gs.n_tasks > gr.n_tasks ? gs.n_tasks : gr.n_tasks;
     // records + slice records (at most one slice record per kSliceRecs records, >= 1 per row)
     const int64_t slices = tasks / kSliceRecs + n_rows + 1;
-    return (tasks + slices) * kNPart * (int64_t)sizeof(double);
+    // (the flat backward and the eval forward write at most kFlatCapMax per-CTA records)
+    return (tasks + slices + kFlatCapMax) * kNPart * (int64_t)sizeof(double);
 }
 
 int64_t mhaq_fq_ticket_count(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
@@ -1110,21 +1411,31 @@ int mhaq_fq_fwd_f32(const float *x, float *y, float *codes, const float *scale, 
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(g.n_tasks);
     const bool clamp = has_clamp(param_mode, lo, hi);
+    if (minmax_ws) {      // eval statistics: persistent, one record per CTA
+        const int eg = eval_grid(g.n_tasks);
+        if (vec && clamp)
+            fq_fwd_kernel<true, true, true><<<eg, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+        else if (vec)
+            fq_fwd_kernel<true, false, true><<<eg, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+        else
+            fq_fwd_kernel<false, true, true><<<eg, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+        return last_error();
+    }
     if (vec && clamp)
-        fq_fwd_kernel<true, true><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+        fq_fwd_kernel<true, true, false><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, nullptr);
     else if (vec)
-        fq_fwd_kernel<true, false><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+        fq_fwd_kernel<true, false, false><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, nullptr);
     else
-        fq_fwd_kernel<false, true><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+        fq_fwd_kernel<false, true, false><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, nullptr);
     return last_error();
 }
 
-int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_inner, float *out3,
+int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_inner, float *out5,
                             void *stream) {
-    if (!minmax_ws || !out3) return MHAQ_FQ_ENULL;
+    if (!minmax_ws || !out5) return MHAQ_FQ_ENULL;
     const int64_t n_tasks = mhaq_fq_num_tasks(n_rows, n_inner);
     if (n_tasks <= 0) return MHAQ_FQ_EINVAL;
-    fq_minmax_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(minmax_ws, n_tasks, out3);
+    fq_minmax_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(minmax_ws, eval_grid(n_tasks), out5);
     return last_error();
 }
 
@@ -1179,14 +1490,60 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets, const float *sca
     const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode};
     const Geom g = reduce_geom(n_rows, n_inner, n_ch);
     const int64_t n_sl = n_slices_of(g);
-    if (n_sl > 65535 * 32 || n_ch > 65535) return MHAQ_FQ_EINVAL;
-    dim3 grid((unsigned)n_sl, (unsigned)n_ch);
+    if (n_sl * n_ch > 0x7fffffffLL) return MHAQ_FQ_EINVAL;
+    const unsigned grid = (unsigned)(n_sl * n_ch);
     double *slice_ws = ws + g.n_tasks * kNPart;
     const int64_t recs = (g.n_rows / g.n_ch) * g.tasks_per_row;
     const int threads = recs <= 64 ? 64 : (recs <= 128 ? 128 : kFinThreads);
-    fq_bwd_finalize_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(ws, slice_ws, tickets, g, prm,
-                                                                    g_scale, g_zp, g_lo, g_hi);
+    fq_bwd_finalize_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(ws, slice_ws, tickets, g, n_sl,
+                                                                    prm, g_scale, g_zp, g_lo, g_hi);
     return last_error();
+}
+
+int mhaq_fq_bwd_single_launch(int64_t n_rows, int64_t n_inner, int64_t n_ch, int method,
+                                 int go_is_code_grad) {
+    return flat_shape_ok(n_rows, n_inner, n_ch, method, go_is_code_grad) ? 1 : 0;
+}
+
+int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx, const float *scale,
+                          const float *zp, const float *lo, const float *hi, int scale_stride,
+                          int zp_stride, int lo_stride, int hi_stride, int param_mode, int64_t n_rows,
+                          int64_t n_inner, int64_t n_ch, int method, int go_is_code_grad, const float *r,
+                          uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                          const float *aewgs_stats, double *ws, unsigned int *tickets, float *g_scale,
+                          float *g_zp, float *g_lo, float *g_hi, void *stream) {
+    int rc = check_common(x, scale, zp, n_rows, n_inner, n_ch);
+    if (rc) return rc;
+    if ((rc = check_mode(param_mode, lo, n_ch)) != 0) return rc;
+    if (!go || !ws || !tickets) return MHAQ_FQ_ENULL;
+    if (n_rows == 0 || n_inner == 0) return 0;
+    const bool aligned = aligned16(x) && aligned16(go) && (!gx || aligned16(gx)) && (!r || aligned16(r));
+    if (aligned && flat_shape_ok(n_rows, n_inner, n_ch, method, go_is_code_grad)) {
+        if (!stride_ok(scale_stride) || !stride_ok(zp_stride) || !stride_ok(lo_stride) ||
+            !stride_ok(hi_stride))
+            return MHAQ_FQ_EINVAL;
+        const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode};
+        const FlatGeom f = make_flat_geom(n_inner, flat_cap());
+        const bool clamp = has_clamp(param_mode, lo, hi);
+        cudaStream_t st = (cudaStream_t)stream;
+        const bool er = (r != nullptr);
+        if (method == MHAQ_FQ_STE)
+            return clamp ? launch_bwd_flat<MHAQ_FQ_STE, true>(er, f, st, go, x, gx, prm, r, seed, offset, philox_dev,
+                                                              ws, tickets, g_scale, g_zp, g_lo, g_hi)
+                         : launch_bwd_flat<MHAQ_FQ_STE, false>(er, f, st, go, x, gx, prm, r, seed, offset, philox_dev,
+                                                               ws, tickets, g_scale, g_zp, g_lo, g_hi);
+        return clamp ? launch_bwd_flat<MHAQ_FQ_LSQ, true>(er, f, st, go, x, gx, prm, r, seed, offset, philox_dev,
+                                                          ws, tickets, g_scale, g_zp, g_lo, g_hi)
+                     : launch_bwd_flat<MHAQ_FQ_LSQ, false>(er, f, st, go, x, gx, prm, r, seed, offset, philox_dev,
+                                                           ws, tickets, g_scale, g_zp, g_lo, g_hi);
+    }
+    rc = mhaq_fq_bwd_f32(go, x, gx, scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride,
+                         param_mode, n_rows, n_inner, n_ch, method, go_is_code_grad, r, seed, offset,
+                         philox_dev, aewgs_stats, ws, stream);
+    if (rc) return rc;
+    return mhaq_fq_bwd_finalize_f32(ws, tickets, scale, zp, lo, hi, scale_stride, zp_stride, lo_stride,
+                                    hi_stride, param_mode, n_rows, n_inner, n_ch, g_scale, g_zp, g_lo,
+                                    g_hi, stream);
 }
 
 int mhaq_fq_aewgs_stats_f32(const float *go, const float *x, const float *scale, const float *zp,

@@ -166,25 +166,74 @@ def _prep_param(p, x: torch.Tensor, name: str):
     return p, (0 if p.numel() == 1 else 1)
 
 
+_ws_bytes_cache = {}
+
+
+def _ws_bytes(geo: Geometry) -> int:
+    key = (geo.n_rows, geo.n_inner)
+    v = _ws_bytes_cache.get(key)
+    if v is None:
+        if len(_ws_bytes_cache) > 4096:
+            _ws_bytes_cache.clear()
+        v = _ws_bytes_cache[key] = int(lib.mhaq_fq_workspace_bytes(geo.n_rows, geo.n_inner))
+    return v
+
+
 def _workspace(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
-    nbytes = lib.mhaq_fq_workspace_bytes(geo.n_rows, geo.n_inner)
-    return torch.empty(nbytes // 8, dtype=torch.float64, device=x.device)
+    """A fresh scratch buffer (callers that keep several in flight, CUDA-graph capture)."""
+    return torch.empty(_ws_bytes(geo) // 8, dtype=torch.float64, device=x.device)
 
 
-# Ticket counters of the deterministic finalize kernel: zero on entry, restored to zero by
-# the kernel, so ONE zero-initialised buffer per (device, stream) is reused by every call
-# ordered on that stream (include/mhaq_fq.h).
-_ticket_bufs = {}
+# Per-(device, stream) scratch of the backward pass.  Calls ordered on one stream may share
+# the record workspace (kernel k+1 writes it after finalize k has read it) and the ticket
+# counters (zero on entry, restored to zero by the kernel: include/mhaq_fq.h), so the eager
+# training path allocates nothing per call.  Bounded: the least recently used stream's entry is
+# dropped beyond _ARENA_MAX streams.
+_ARENA_MAX = 16
+_arenas = {}
+
+
+class _Arena:
+    __slots__ = ("ws", "tickets")
+
+    def __init__(self):
+        self.ws = None
+        self.tickets = None
+
+
+def _arena(x: torch.Tensor) -> _Arena:
+    key = (x.device.index, torch._C._cuda_getCurrentRawStream(x.device.index))
+    a = _arenas.get(key)
+    if a is None:
+        if len(_arenas) >= _ARENA_MAX:
+            _arenas.pop(next(iter(_arenas)))
+        a = _arenas[key] = _Arena()
+    elif len(_arenas) > 1:
+        _arenas[key] = _arenas.pop(key)          # most recently used last
+    return a
 
 
 def _tickets(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
-    need = lib.mhaq_fq_ticket_count(geo.n_rows, geo.n_inner, geo.n_ch)
-    key = (x.device.index, torch._C._cuda_getCurrentRawStream(x.device.index))
-    buf = _ticket_bufs.get(key)
+    need = geo.n_ch if geo.n_ch > 0 else 1       # == mhaq_fq_ticket_count
+    a = _arena(x)
+    buf = a.tickets
     if buf is None or buf.numel() < need:
         n = max(4096, 1 << (int(need) - 1).bit_length())
-        buf = torch.zeros(n, dtype=torch.int32, device=x.device)
-        _ticket_bufs[key] = buf
+        buf = a.tickets = torch.zeros(n, dtype=torch.int32, device=x.device)
+    return buf
+
+
+def _shared_workspace(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
+    """The stream's reusable record workspace; a private buffer while a CUDA graph is being
+    captured (a captured call must not alias scratch that eager calls keep using)."""
+    if torch.cuda.is_current_stream_capturing():
+        return _workspace(x, geo)
+    need = _ws_bytes(geo) // 8
+    a = _arena(x)
+    buf = a.ws
+    if buf is None or buf.numel() < need:
+        n = max(1 << 15, 1 << (int(need) - 1).bit_length())
+        buf = a.ws = torch.empty(n, dtype=torch.float64, device=x.device)
     return buf
 
 
@@ -227,7 +276,7 @@ def reset_philox_call_counter() -> None:
         _philox_call[k] = 0
 
 
-PARAMS_LINEAR, PARAMS_ACT_LOG, PARAMS_WEIGHT_LOG = 0, 1, 2
+PARAMS_LINEAR, PARAMS_ACT_LOG, PARAMS_WEIGHT_LOG, PARAMS_UNIT = 0, 1, 2, 3
 
 
 class _Launch:
@@ -284,6 +333,21 @@ class _Launch:
             raise RuntimeError("per-channel weight parameters must have one entry per row of dim 0")
         return L
 
+    @classmethod
+    def unit(cls, v, scale):
+        """MHAQ_FQ_PARAMS_UNIT: `v` is already scaled (the two-step `v + QN*.apply(v, s)` form);
+        `scale` only fixes the channel layout of the estimator's scale gradient."""
+        _require_cuda(v)
+        L = cls.__new__(cls)
+        L.mode = PARAMS_UNIT
+        L.geo = infer_geometry(v, [scale])
+        L.scale, L.ss = _prep_param(scale, v, "scale")
+        L.zp, L.zs = L.scale, L.ss
+        L.lo = L.hi = None
+        L.ls = L.hs = 0
+        L.stats_over_all = (scale.dim() > 0 and scale.numel() > 1 and all(n != 1 for n in scale.shape))
+        return L
+
     def params(self):
         return (_ptr(self.scale), _ptr(self.zp), _ptr(self.lo), _ptr(self.hi),
                 self.ss, self.zs, self.ls, self.hs, self.mode)
@@ -302,10 +366,19 @@ def _forward_impl(x, L: _Launch, want_y: bool, want_codes: bool, want_minmax: bo
                                   geo.n_rows, geo.n_inner, geo.n_ch, _ptr(ws), _stream()),
               "mhaq_fq_fwd_f32")
         if want_minmax:
-            mm = torch.empty(3, dtype=torch.float32, device=x.device)
+            mm = torch.empty(5, dtype=torch.float32, device=x.device)
             check(lib.mhaq_fq_minmax_finalize(_ptr(ws), geo.n_rows, geo.n_inner, _ptr(mm), _stream()),
                   "mhaq_fq_minmax_finalize")
     return y, codes, mm
+
+
+def launches_per_fwd_bwd(x, scale, zp, lo, hi, method) -> int:
+    """How many kernels of this library one fake_quant forward + backward launches for these
+    operands: forward, backward, finalize (+ the AEWGS statistics kernel and its finalize)."""
+    mid = _method_id(method)
+    geo = infer_geometry(x, [p for p in (scale, zp, lo, hi) if torch.is_tensor(p)])
+    single = lib.mhaq_fq_bwd_single_launch(geo.n_rows, geo.n_inner, geo.n_ch, mid, 0)
+    return (2 if single else 3) + (2 if mid == METHOD_IDS["AEWGS"] else 0)
 
 
 def _reduce_to_param(g: torch.Tensor, param, geo: Geometry, x_shape):
@@ -380,19 +453,22 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
         return gx, torch.zeros(4, n_ch, dtype=torch.float32, device=x.device)
     out = torch.empty(4, n_ch, dtype=torch.float32, device=x.device)   # fully written by the kernel
     if method == METHOD_IDS["AEWGS"] and geo.axis is None and x.dim() >= 2 and L.scale.dim() == 1:
+        if L.mode not in (PARAMS_LINEAR, PARAMS_UNIT):
+            # (the log-domain modes return log-domain gradients of ONE channel; the dim-0 quirk
+            # needs per-position channels — the layers route AEWGS through the linear operands)
+            raise NotImplementedError("per-tensor AEWGS needs the linear parameter mode")
         return _backward_aewgs_dim0(go, x, L, code_grad, noise, need_gx, philox)
     stats = aewgs_stats(go, x, L, code_grad) if method == METHOD_IDS["AEWGS"] else None
-    ws = _workspace(x, geo)
+    ws = _shared_workspace(x, geo)
     noise, seed, offset, pdev = _noise_source(x, method, noise, philox)
     tk = _tickets(x, geo)
-    check(lib.mhaq_fq_bwd_f32(_ptr(go), _ptr(x), _ptr(gx), *L.params(),
-                              geo.n_rows, geo.n_inner, geo.n_ch, method, int(code_grad),
-                              _ptr(noise), seed, offset, _ptr(pdev), _ptr(stats), _ptr(ws), _stream()),
-          "mhaq_fq_bwd_f32")
-    check(lib.mhaq_fq_bwd_finalize_f32(_ptr(ws), _ptr(tk), *L.params(), geo.n_rows, geo.n_inner,
-                                       geo.n_ch, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]),
-                                       _ptr(out[3]), _stream()),
-          "mhaq_fq_bwd_finalize_f32")
+    # one C call: backward + deterministic reduction (ONE kernel for per-tensor STE / LSQ,
+    # otherwise the streaming backward followed by the finalize kernel)
+    check(lib.mhaq_fq_bwd_fused_f32(_ptr(go), _ptr(x), _ptr(gx), *L.params(),
+                                    geo.n_rows, geo.n_inner, geo.n_ch, method, int(code_grad),
+                                    _ptr(noise), seed, offset, _ptr(pdev), _ptr(stats), _ptr(ws), _ptr(tk),
+                                    _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream()),
+          "mhaq_fq_bwd_fused_f32")
     return gx, out
 
 
@@ -407,6 +483,7 @@ def _backward_aewgs_dim0(go, x, L: _Launch, code_grad, noise, need_gx, philox):
     got = go.reshape(O_, P_).t().contiguous()
     nt = None if noise is None else noise.reshape(O_, P_).t().contiguous()
     Lt = _Launch.__new__(_Launch)
+    Lt.mode = L.mode
     Lt.geo = Geometry(P_, O_, P_, 0)
     Lt.scale, Lt.ss, Lt.zp, Lt.zs = L.scale, 0, L.zp, 0
     Lt.lo, Lt.ls, Lt.hi, Lt.hs = L.lo, 0, L.hi, 0
@@ -488,6 +565,42 @@ def quantize_eval(x, scale, zero_point, min_val=None, max_val=None, want_y=True,
     x = x.detach()
     L = _Launch(x, scale, zero_point, min_val, max_val)
     return _forward_impl(_dense(x, L.geo.axis), L, want_y, want_codes, True)
+
+
+class _RoundingNoiseFn(torch.autograd.Function):
+    """The reference's QNoise family (gdnsq.py:11-147) as a stand-alone op: forward
+    ``round(v) - v`` on an already-scaled value, backward the estimator's (grad_v, grad_scale)."""
+
+    @staticmethod
+    def forward(ctx, v, scale, method, noise, philox):
+        L = _Launch.unit(v, scale)
+        v = v.contiguous() if method == METHOD_IDS["AEWGS"] and L.geo.axis is None else _dense(v, L.geo.axis)
+        _, codes, _ = _forward_impl(v, L, want_y=False, want_codes=True, want_minmax=False)
+        ctx.save_for_backward(v, scale)
+        ctx.L, ctx.method, ctx.noise, ctx.philox = L, method, noise, philox
+        return codes.sub_(v) if codes is not None else torch.empty_like(v)
+
+    @staticmethod
+    def backward(ctx, go):
+        v, scale = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        # codes = v + noise: the backward kernel, fed d/d codes = go, returns d codes/dv * go;
+        # the identity branch (the `v +` of gdnsq.py:208) is not part of this op
+        gx, out = _backward_impl(go, v, ctx.L, ctx.method, True, ctx.noise, need[0], ctx.philox)
+        gv = None
+        if need[0]:
+            gv = gx.sub_(_like_layout(go, v))
+        gs = _reduce_to_param(out[0], scale, ctx.L.geo, v.shape) if need[1] else None
+        return gv, gs, None, None, None
+
+
+def rounding_noise(v, scale, method="STE", noise=None, philox=None):
+    """``QN<method>.apply(v, scale)`` of the reference: ``round(v) - v`` with the estimator's
+    gradients (gdnsq.py:35-57 STE, 63-84 LSQ, 90-107 EWGS, 113-147 AEWGS)."""
+    _require_cuda(v)
+    if not torch.is_tensor(scale):
+        scale = torch.full((1,), float(scale), dtype=torch.float32, device=v.device)
+    return _RoundingNoiseFn.apply(v, scale, _method_id(method), noise, philox)
 
 
 def philox_noise(shape_like: torch.Tensor, scale_like=None, seed: int = 0, offset: int = 0):

@@ -3,9 +3,11 @@
 `MinMaxObserver` records the running min / max of every NoisyAct input;
 `apply_mean_stats_activations` turns them into (act_b, log_act_s, log_act_q);
 `apply_quantile_weights_s` raises every weight scale to at least range / (2^bits - 1).
-SURVEY.md §8 row (f)-2.  Differences that do not change results: one `aminmax` pass per batch
-instead of separate `min` and `max` passes plus a `torch.cat`, and running min/max tensors
-instead of growing lists (the reference only ever takes `.min()` / `.max()` of them).
+SURVEY.md §8 row (f)-2.  Differences that do not change results: the input's min / max come
+out of the NoisyAct eval forward kernel itself (fused epilogue, `mhaq_fq_minmax_finalize`; one
+`aminmax` pass as fall-back for a disabled quantizer) instead of separate `min` and `max` passes
+plus a `torch.cat` per batch, and running min/max tensors instead of growing lists (the reference
+only ever takes `.min()` / `.max()` of them).
 Like the reference, calibration RE-BINDS the parameters to new `nn.Parameter` objects
 (minmaxobserver.py:59-66, 86) — the layers' weight cache is keyed to survive that.
 """
@@ -26,8 +28,15 @@ class MinMaxObserver(ObserverHook):
         return self._hook(module, input, output)
 
     def _hook(self, module, input, output) -> None:
-        mm = input[0].detach().aminmax()
-        mn, mx = mm.min.reshape(1), mm.max.reshape(1)
+        x = input[0]
+        fused = getattr(module, "_in_minmax", None)
+        if fused is not None and fused[:3] == (x.data_ptr(), x._version, tuple(x.shape)):
+            # the eval forward kernel of this NoisyAct already reduced this very tensor
+            # (min / max input ride along with min / max code): no extra pass
+            mn, mx = fused[3][0:1], fused[3][1:2]
+        else:
+            mm = x.detach().aminmax()
+            mn, mx = mm.min.reshape(1), mm.max.reshape(1)
         prev_mn = getattr(module, "min_values", None)
         if prev_mn is None or prev_mn.numel() == 0:
             module.min_values, module.max_values = mn, mx

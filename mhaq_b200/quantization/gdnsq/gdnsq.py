@@ -9,11 +9,13 @@ the fused ``dequantize(quantize(x))`` the layer wrappers call (one kernel each
 way instead of ~8 / ~19-27 ATen launches).
 
 The reference's ``QNoise`` / ``QNSTE`` / ``QNLSQ`` / ``QNEWGS`` / ``QNAEWGS``
-autograd Functions (gdnsq.py:11-147) have no separate existence here: their
-forward (``round(v) - v``) and backward are fused into ``mhaq_fq_fwd_f32`` /
-``mhaq_fq_bwd_f32``.  The names are kept importable; calling them raises.
+autograd Functions (gdnsq.py:11-147) are fused into ``mhaq_fq_fwd_f32`` /
+``mhaq_fq_bwd_f32``; the names stay importable and ``apply`` keeps working through
+``ops.rounding_noise`` (the two-step ``v + QN*.apply(v, s)`` form).
 """
 from __future__ import annotations
+
+from enum import Enum
 
 import torch
 from torch import Tensor
@@ -28,34 +30,37 @@ def reduce_to_shape(t: Tensor, like: Tensor) -> Tensor:
     return torch.mean(t, dim=dims, keepdim=True)
 
 
-class _Fused:
-    """Placeholder for an autograd Function of the reference that is fused into the kernels."""
+class QNoise:
+    """The reference's rounding-noise autograd Functions (gdnsq.py:11-147): ``apply(v, s)`` returns
+    ``round(v) - v`` and its backward is the estimator's (``grad_v``, ``grad_s``).  In this package
+    they are fused into the kernels; ``apply`` is kept working for callers of the two-step form
+    (``v + QN*.apply(v, s)``, gdnsq.py:206-208, and ``scaled_noise``): it runs the forward kernel on
+    the already-scaled value (zero point 0, unit divisor) and returns ``codes - v``, so the codes are
+    bit-identical and autograd sees d(noise)/dv = estimator - 1, d(noise)/ds = the estimator's
+    scale gradient, exactly the reference's (backward kernel with the code gradient as input).
+    ``QNoise.apply`` itself raises in backward in the reference (gdnsq.py:26-29); here it behaves
+    like QNSTE."""
+    _method = "STE"
 
     @classmethod
-    def apply(cls, *a, **k):
-        raise NotImplementedError(
-            f"{cls.__name__} is fused into the sm_100a kernels (mhaq_fq_fwd_f32 / mhaq_fq_bwd_f32); "
-            "use Quantizer.quantize / Quantizer.fake_quant")
-
-
-class QNoise(_Fused):
-    pass
+    def apply(cls, value, scale):
+        return ops.rounding_noise(value, scale, method=cls._method)
 
 
 class QNSTE(QNoise):
-    pass
+    _method = "STE"
 
 
 class QNLSQ(QNoise):
-    pass
+    _method = "LSQ"
 
 
 class QNEWGS(QNoise):
-    pass
+    _method = "EWGS"
 
 
 class QNAEWGS(QNoise):
-    pass
+    _method = "AEWGS"
 
 
 def scaled_noise(x, s):
@@ -109,9 +114,16 @@ class Quantizer:
 
     # -- helpers ---------------------------------------------------------------------------
     def _method(self):
-        if not isinstance(self.qnmethod, QNMethod):
-            raise AttributeError(f"Unknown method {self.qnmethod}!")
-        return self.qnmethod
+        """The estimator as this package's QNMethod.  Another package's enum with the same
+        name AND value is accepted — the reference's own `QNMethod` when its `GDNSQQuant`
+        constructs these layer classes; anything else raises like
+        gdnsq.py:240-241."""
+        m = self.qnmethod
+        if isinstance(m, QNMethod):
+            return m
+        if isinstance(m, Enum) and m.name in QNMethod.__members__ and QNMethod[m.name].value == m.value:
+            return QNMethod[m.name]
+        raise AttributeError(f"Unknown method {self.qnmethod}!")
 
     def _zp_like(self, value):
         zp = self.zero_point
@@ -157,8 +169,7 @@ class Quantizer:
         return quantized_value * self.scale + self.zero_point
 
     def _get_rnoise(self, value: Tensor, scale: Tensor):
-        self._method()
-        return QNoise.apply(value, scale)
+        return {"STE": QNSTE, "EWGS": QNEWGS, "AEWGS": QNAEWGS, "LSQ": QNLSQ}[self._method().name].apply(value, scale)
 
     # -- fused entry -----------------------------------------------------------------------
     def fake_quant(self, value, noise=None):

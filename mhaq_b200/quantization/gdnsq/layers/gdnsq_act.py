@@ -42,7 +42,11 @@ class NoisyAct(nn.Module):
     def forward(self, x):
         if self.disable:
             return x
-        if self.training and self.Q.positive_scale and x.is_cuda:
+        self._in_minmax = None
+        if (self.training and self.Q.positive_scale and x.is_cuda
+                and self.Q._method().name != "AEWGS"):
+            # (AEWGS on a per-tensor quantizer follows the reference's dim-0 statistics quirk,
+            # which needs the linear operands: it takes the generic route below)
             # fused: the kernels read log_act_s / log_act_q / act_b themselves and return the
             # log-domain gradients; Q.scale & co. are materialised only if somebody reads them
             self.Q.defer(self._operands)
@@ -59,6 +63,9 @@ class NoisyAct(nn.Module):
             y, mm = self.Q.fake_quant_eval(x)
         self.Q._assert_valid(mm)
         self.bw = torch.log2(mm[1] - mm[0] + 1)
+        # the same pass also took min / max of the INPUT (mm[3], mm[4]): what a MinMaxObserver
+        # forward hook wants from this very tensor during calibration (calib/minmaxobserver.py)
+        self._in_minmax = (x.data_ptr(), x._version, tuple(x.shape), mm[3:5])
         if needs_graph:
             return self.Q.fake_quant(x)
         return y

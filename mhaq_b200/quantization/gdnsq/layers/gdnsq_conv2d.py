@@ -10,7 +10,7 @@ a non-trainable ``(1,)`` Parameter kept for state-dict compatibility.
 import torch
 from torch import nn, inf
 
-from ....aux.types import QScheme
+from ....aux.types import QScheme, is_per_channel, is_per_tensor
 from ....aux.qutils import is_biased
 from ..gdnsq import Quantizer
 from ..gdnsq_utils import QNMethod
@@ -26,9 +26,9 @@ class NoisyConv2d(nn.Conv2d):
         super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups,
                          bias, padding_mode, device, dtype)
         self.qscheme = qscheme
-        if self.qscheme == QScheme.PER_TENSOR:
+        if is_per_tensor(self.qscheme):
             self.log_wght_s = nn.Parameter(torch.Tensor([log_s_init]), requires_grad=True)
-        elif self.qscheme == QScheme.PER_CHANNEL:
+        elif is_per_channel(self.qscheme):
             self.log_wght_s = nn.Parameter(torch.empty((out_channels, 1, 1, 1)).fill_(log_s_init),
                                            requires_grad=True)
             self.log_b_s = nn.Parameter(torch.empty(1).fill_(log_s_init), requires_grad=True)
@@ -62,7 +62,7 @@ class NoisyConv2d(nn.Conv2d):
         if hit is not None:
             return hit
         mx = lr = None
-        if self.qscheme == QScheme.PER_CHANNEL and self.positive_scale_ok():
+        if is_per_channel(self.qscheme) and self.positive_scale_ok():
             # fused: row min (zero point) + row max in one pass, quantization in the next, the
             # scale taken in the log domain (no exp2 / Exp2Backward launches)
             weight, mn_flat, mx, lr = self.Q.fake_quant_weight(self.weight, log_scale=self.log_wght_s)
@@ -70,7 +70,7 @@ class NoisyConv2d(nn.Conv2d):
         else:
             s = torch.exp2(self.log_wght_s)
             self.Q.scale = s
-            if self.qscheme == QScheme.PER_CHANNEL:
+            if is_per_channel(self.qscheme):
                 mn = self.weight.amin((1, 2, 3), keepdim=True)
             else:
                 mn = self.weight.amin()

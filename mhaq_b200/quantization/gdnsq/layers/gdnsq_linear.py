@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn, inf
 
-from ....aux.types import QScheme
+from ....aux.types import QScheme, is_per_channel, is_per_tensor
 from ....aux.qutils import is_biased
 from ..gdnsq import Quantizer
 from ..gdnsq_utils import QNMethod
@@ -25,9 +25,9 @@ class NoisyLinear(nn.Linear):
                  rand_noise: bool = False, qnmethod: QNMethod = QNMethod.STE) -> None:
         super().__init__(in_features, out_features, bias, device, dtype)
         self.qscheme = qscheme
-        if self.qscheme == QScheme.PER_TENSOR:
+        if is_per_tensor(self.qscheme):
             self.log_wght_s = nn.Parameter(torch.Tensor([log_s_init]), requires_grad=True)
-        elif self.qscheme == QScheme.PER_CHANNEL:
+        elif is_per_channel(self.qscheme):
             self.log_wght_s = nn.Parameter(torch.empty((out_features, 1, 1, 1)).fill_(log_s_init),
                                            requires_grad=True)
         self._noise_ratio = nn.Parameter(torch.Tensor([1]), requires_grad=False)
@@ -52,7 +52,7 @@ class NoisyLinear(nn.Linear):
                                          self.training)
         if hit is not None:
             return hit
-        if self.qscheme == QScheme.PER_CHANNEL:
+        if is_per_channel(self.qscheme):
             if self.Q.positive_scale and self.weight.is_cuda:
                 out = self.Q.fake_quant_weight(self.weight, log_scale=self.log_wght_s)
             else:

@@ -5,7 +5,7 @@ log-domain scale parameters and the differentiable weight range
 import torch
 from torch import nn
 
-from ....aux.types import QScheme
+from ....aux.types import QScheme, is_per_channel, is_per_tensor
 from ..layers.gdnsq_act import NoisyAct
 from ..layers.gdnsq_conv2d import NoisyConv2d
 from ..layers.gdnsq_linear import NoisyLinear
@@ -19,7 +19,7 @@ class ModelHelper:
             if isinstance(m, (NoisyConv2d, NoisyLinear)):
                 if not m.log_wght_s.requires_grad:
                     continue
-                if qscheme == QScheme.PER_CHANNEL:
+                if is_per_channel(qscheme):
                     dims = tuple(range(1, m.weight.dim()))
                     log_wght_s.append(m.log_wght_s.ravel())
                     # the layer already reduced the weight rows in this step's forward: the
@@ -42,7 +42,7 @@ class ModelHelper:
                 if m.log_act_s.requires_grad:
                     log_act_q.append(m.log_act_q)
                     log_act_s.append(m.log_act_s)
-        if qscheme == QScheme.PER_TENSOR:
+        if is_per_tensor(qscheme):
             return (torch.stack(log_act_s).ravel(), torch.stack(log_act_q).ravel(),
                     torch.stack(log_wght_s).ravel(), torch.stack(log_w_n_b).ravel())
         return (torch.cat(log_act_s), torch.cat(log_act_q), torch.cat(log_wght_s),

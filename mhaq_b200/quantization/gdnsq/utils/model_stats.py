@@ -4,7 +4,7 @@ src/quantization/gdnsq/utils/model_stats.py:116-262, computed with tensor ops on
 SURVEY.md §8 row (f)-3: not on the training hot path."""
 import torch
 
-from ....aux.types import QScheme
+from ....aux.types import QScheme, is_per_channel, is_per_tensor
 from ..layers.gdnsq_act import NoisyAct
 from ..layers.gdnsq_conv2d import NoisyConv2d
 from ..layers.gdnsq_linear import NoisyLinear
@@ -22,7 +22,7 @@ def _code_span_bits(module) -> torch.Tensor:
         if hasattr(module, "quantized_weight"):
             module.quantized_weight()            # refresh Q.scale / Q.zero_point
         codes = module.Q.quantize(module.weight.detach())
-        if module.qscheme == QScheme.PER_CHANNEL:
+        if is_per_channel(module.qscheme):
             flat = codes.reshape(codes.shape[0], -1)
             return torch.log2(flat.amax(1) - flat.amin(1) + 1)
         return torch.log2(codes.max() - codes.min() + 1).reshape(1)
@@ -30,7 +30,7 @@ def _code_span_bits(module) -> torch.Tensor:
 
 def get_true_layer_bit_width(module, max=True):
     bits = _code_span_bits(module)
-    return bits.max() if (max or module.qscheme == QScheme.PER_TENSOR) else bits.mean()
+    return bits.max() if (max or is_per_tensor(module.qscheme)) else bits.mean()
 
 
 def get_true_weights_width(model, max=True):
@@ -46,7 +46,7 @@ def get_true_activations_width(model, max=True):
 
 
 def get_layer_wnb_bit_width(layer_weights, log_s, config=QScheme.PER_TENSOR):
-    if config == QScheme.PER_TENSOR:
+    if is_per_tensor(config):
         mn, mx = layer_weights.amin(), layer_weights.amax()
     else:
         dims = tuple(range(1, layer_weights.dim()))

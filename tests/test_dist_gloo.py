@@ -97,7 +97,9 @@ def test_bench_reference_arm_under_torchrun_two_ranks():
     assert len(lines) == 1, out.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["unit"] == "GB/s"
-    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["steps"] == 1 and d["warmup"] == 1          # the arm runs exactly the steps it was asked for
+    assert d["product_modules_loaded"] == []             # nothing of the product in the reference process
 
 
 class _ToyQuantLayer(torch.nn.Module):

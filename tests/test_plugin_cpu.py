@@ -79,10 +79,60 @@ def test_unknown_estimator_name():
         Quantizer(cfg)().quantize(lm)
 
 
-def test_fused_functions_are_placeholders():
-    from mhaq_b200.quantization.gdnsq.gdnsq import QNSTE
-    with pytest.raises(NotImplementedError, match="fused"):
-        QNSTE.apply(torch.zeros(2), torch.ones(1))
+def test_rounding_noise_functions_route_to_the_kernels_and_refuse_cpu_tensors():
+    # QNSTE & co. (gdnsq.py:32-147) stay callable: they run the kernels (ops.rounding_noise);
+    # like every other entry point they refuse CPU tensors instead of falling back
+    from mhaq_b200.quantization.gdnsq.gdnsq import QNSTE, QNLSQ, QNEWGS, QNAEWGS, scaled_noise
+    for fn in (QNSTE.apply, QNLSQ.apply, QNEWGS.apply, QNAEWGS.apply, scaled_noise):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fn(torch.zeros(2), torch.ones(1))
+
+
+def test_layers_accept_the_reference_packages_own_enums():
+    # the reference's GDNSQQuant constructs these classes with ITS enums
+    import enum
+    RefQScheme = enum.Enum("QScheme", {"PER_TENSOR": 0, "PER_CHANNEL": 1})
+    RefQN = enum.Enum("QNMethod", {"STE": 0, "EWGS": 1, "AEWGS": 2, "LSQ": 3})
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
+    c = NoisyConv2d(4, 8, 3, qscheme=RefQScheme.PER_CHANNEL, qnmethod=RefQN.LSQ)
+    assert c.log_wght_s.shape == (8, 1, 1, 1) and hasattr(c, "log_b_s")
+    assert c.qscheme is RefQScheme.PER_CHANNEL                # stored as given
+    assert c.Q._method().name == "LSQ"
+    c = NoisyConv2d(4, 8, 3, qscheme=RefQScheme.PER_TENSOR, qnmethod=RefQN.STE)
+    assert c.log_wght_s.shape == (1,)
+    Bad = enum.Enum("QNMethod", {"STE": 7})
+    c.Q.qnmethod = Bad.STE
+    with pytest.raises(AttributeError, match="Unknown method"):
+        c.Q._method()
+
+
+def test_src_alias_resolves_the_reference_import_paths():
+    # run in a fresh interpreter: the alias must not collide with a loaded reference `src`
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import mhaq_b200.compat as c; names = c.install_src_alias()\n"
+        "from src.quantization.quantizer import Quantizer\n"
+        "from src.quantization.gdnsq.gdnsq_quant import GDNSQQuant\n"
+        "from src.quantization.gdnsq.layers.gdnsq_act import NoisyAct\n"
+        "from src.quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d\n"
+        "from src.quantization.gdnsq.layers.gdnsq_linear import NoisyLinear\n"
+        "from src.quantization.gdnsq.utils.model_helper import ModelHelper\n"
+        "from src.quantization.gdnsq.utils import model_stats\n"
+        "from src.quantization.gdnsq.calib.minmaxobserver import MinMaxObserver, apply_mean_stats_activations, apply_quantile_weights_s\n"
+        "from src.quantization.gdnsq.calib.hooks import register_lightning_activation_forward_hook\n"
+        "from src.quantization.gdnsq.config.config_schema import GDNSQQuantizerParams\n"
+        "from src.quantization.gdnsq.gdnsq import Quantizer as Q, QNoise, QNSTE, QNLSQ, QNEWGS, QNAEWGS, reduce_to_shape, scaled_noise\n"
+        "from src.quantization.gdnsq.gdnsq_utils import QNMethod, QMode\n"
+        "from src.aux.types import QScheme, QMethod, MType, DType\n"
+        "from src.aux.qutils import attrsetter, is_biased\n"
+        "import src.quantization as pkg, mhaq_b200.quantization as real\n"
+        "assert pkg is real and pkg.GDNSQQuant is GDNSQQuant\n"
+        "import mhaq_b200.quantization.gdnsq.layers.gdnsq_act as a; assert a.NoisyAct is NoisyAct\n"
+        "print('ok', len(names))\n" % root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stderr[-1500:]
 
 
 def test_cpu_forward_fails_loudly():
