@@ -29,6 +29,8 @@
  *                              MinMaxObserver takes during calibration
  *                              (calib/minmaxobserver.py:28-37) — all from the forward's own pass
  *   mhaq_fq_noise_f32          torch.randint_like(input, 2).sub_(0.5)  (gdnsq.py:54)
+ *   mhaq_fq_potential_loss_*   PotentialLoss.forward's constraint arithmetic and its autograd
+ *                              (gdnsq_loss.py:32-86, 114-168), one launch each way
  *
  * Conventions
  *   - fp32 only, CUDA only, contiguous tensors only.  No CPU fallback exists.
@@ -162,7 +164,7 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets,
 
 /* mhaq_fq_bwd_f32 + mhaq_fq_bwd_finalize_f32 as one entry point (same arguments, the union of
  * the two lists).  For a per-tensor tensor (n_rows = n_ch = 1: every activation) with the
- * STE / LSQ estimator, gradient w.r.t. y and at most 2^26 elements it is ONE kernel: a
+ * STE / LSQ estimator, gradient w.r.t. y and at most 2^25 elements it is ONE kernel: a
  * persistent, balanced grid (<= SMs x 5 blocks, each block one contiguous range) whose last
  * block to finish (ticket) sums the per-block fp64 records in index order and writes the
  * gradients — no second launch, no per-task flushes; bitwise reproducible on a given device.
@@ -230,6 +232,54 @@ int mhaq_fq_wrow_bwd_f32(const float *g_wq, const float *w, const float *log_sca
                          int64_t n_rows, int64_t n_inner, int method,
                          const float *r, uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
                          float *g_w, float *g_log_scale, void *stream);
+
+/* Multi-tensor forms of the two entry points above: EVERY per-channel weight tensor of a model in
+ * one launch each way (CIFAR-sized models are bound by launch count, not
+ * by any kernel).  `descs` is a HOST array; the descriptors travel in the kernel's parameter
+ * space (the library splits more than 32 / 24 tensors over several launches).  Fields have the
+ * meaning of the same-named arguments of mhaq_fq_wrow_fwd_f32 / mhaq_fq_wrow_bwd_f32; tensor i of
+ * the backward draws its in-kernel noise from Philox stream (seed, offset + i) — what a
+ * per-tensor call with that offset would read; `r` must be NULL for all tensors or for none. */
+typedef struct {
+    const float *w, *log_scale;
+    float *wq, *row_min, *row_max, *log_range;      /* any may be NULL */
+    int64_t n_rows, n_inner;
+} mhaq_fq_wrow_fwd_desc;
+typedef struct {
+    const float *g_wq, *w, *log_scale, *row_min, *row_max;
+    const float *g_log_range, *g_row_min, *g_row_max, *r;   /* any may be NULL */
+    float *g_w, *g_log_scale;                               /* either may be NULL */
+    int64_t n_rows, n_inner;
+} mhaq_fq_wrow_bwd_desc;
+int mhaq_fq_wrow_multi_fwd_f32(const mhaq_fq_wrow_fwd_desc *descs, int n_tensors, void *stream);
+int mhaq_fq_wrow_multi_bwd_f32(const mhaq_fq_wrow_bwd_desc *descs, int n_tensors, int method,
+                               uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                               void *stream);
+
+/* PotentialLoss's bit-width constraint (gdnsq_loss.py:32-86 / 114-168, exponent p = 1 as
+ * GDNSQQuant passes it, gdnsq_quant.py:90-102) in ONE launch:
+ *   ploss = (loss_sum/cnt) * l1 * (wmul * wloss + amul * aloss) + l2 * base_loss,
+ *   wloss = mean(max(0, (log_w_range - log_wght_s) - (w_target - eps))),  aloss likewise with
+ *   (log_act_q - log_act_s, a_target); wmul / amul from the numbers of active constraints;
+ *   (l1, l2) = lossless ? (1, t) : (t, 1); when `training`, loss_sum += base_loss and cnt += 1
+ *   (device scalars, updated in place — CUDA-graph friendly).
+ * out: MHAQ_FQ_PLOSS_NOUT floats = {ploss, wloss, aloss, rloss, -mean(log_wght_s),
+ *   mean(log_w_range), -mean(log_act_s), mean(log_act_q), max(log_w_range - log_wght_s), wact, aact,
+ *   cw, ca, l2}; the last three are what the backward needs (pass `out` back as `saved`). */
+#define MHAQ_FQ_PLOSS_NOUT 14
+int mhaq_fq_potential_loss_fwd_f32(const float *log_act_s, const float *log_act_q, int64_t n_act,
+                                   const float *log_wght_s, const float *log_w_range, int64_t n_wght,
+                                   const float *base_loss, float *loss_sum, float *cnt,
+                                   float w_target, float a_target, float eps, float t,
+                                   int lossless, int training, float *out, void *stream);
+/* Gradients of ploss (times g_loss[0]) w.r.t. the four vectors and the base loss; any output may
+ * be NULL.  torch.max(0, x) semantics: full gradient where x > 0, half on a tie. */
+int mhaq_fq_potential_loss_bwd_f32(const float *log_act_s, const float *log_act_q, int64_t n_act,
+                                   const float *log_wght_s, const float *log_w_range, int64_t n_wght,
+                                   const float *saved, const float *g_loss,
+                                   float w_target, float a_target, float eps,
+                                   float *g_log_act_s, float *g_log_act_q, float *g_log_wght_s,
+                                   float *g_log_w_range, float *g_base_loss, void *stream);
 
 /* Materialise the in-kernel noise stream: r[i] in {-0.5,+0.5}, identical to what
  * mhaq_fq_bwd_f32 draws for the same (seed, offset, philox_dev, shape). */

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_int, c_int64, c_uint64, c_void_p, c_char_p
+from ctypes import c_float, c_int, c_int64, c_uint64, c_void_p, c_char_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # MHAQ_FQ_LIB: experiment knob to load an alternative build of the same ABI
@@ -16,6 +16,19 @@ LIB_PATH = os.environ.get("MHAQ_FQ_LIB") or os.path.join(_HERE, "csrc", "libmhaq
 
 ABI_VERSION = 5
 NPART = 8  # MHAQ_FQ_NPART
+
+class WRowFwdDesc(ctypes.Structure):
+    """mhaq_fq_wrow_fwd_desc"""
+    _fields_ = [(n, c_void_p) for n in ("w", "log_scale", "wq", "row_min", "row_max", "log_range")] + [
+        ("n_rows", c_int64), ("n_inner", c_int64)]
+
+
+class WRowBwdDesc(ctypes.Structure):
+    """mhaq_fq_wrow_bwd_desc"""
+    _fields_ = [(n, c_void_p) for n in ("g_wq", "w", "log_scale", "row_min", "row_max", "g_log_range",
+                                        "g_row_min", "g_row_max", "r", "g_w", "g_log_scale")] + [
+        ("n_rows", c_int64), ("n_inner", c_int64)]
+
 
 # name -> (restype, argtypes); mirrors include/mhaq_fq.h one to one
 _P = c_void_p
@@ -45,6 +58,12 @@ _SIGNATURES = {
                                      c_uint64, c_uint64, _P, _P, _P, _P]),
     "mhaq_fq_rowstat_f32": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "mhaq_fq_rowstat_bwd_f32": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mhaq_fq_wrow_multi_fwd_f32": (c_int, [_P, c_int, _P]),
+    "mhaq_fq_wrow_multi_bwd_f32": (c_int, [_P, c_int, c_int, c_uint64, c_uint64, _P, _P]),
+    "mhaq_fq_potential_loss_fwd_f32": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, _P, c_float, c_float,
+                                               c_float, c_float, c_int, c_int, _P, _P]),
+    "mhaq_fq_potential_loss_bwd_f32": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_float, c_float,
+                                               c_float, _P, _P, _P, _P, _P, _P]),
     "mhaq_fq_noise_f32": (c_int, [_P, c_int64, c_int64, c_uint64, c_uint64, _P, _P]),
 }
 

@@ -785,23 +785,47 @@ constexpr int kFlatGroup = 4;                     // batches between fp32 -> fp6
 constexpr int kFlatCapMax = 2048;                 // upper bound on the grid (workspace sizing)
 
 struct FlatGeom {
-    int64_t n;         // elements
-    int64_t full;      // full batches
-    int64_t per_cta;   // batches per block
-    int grid;          // blocks == records
+    int64_t n;          // elements
+    int64_t full;       // whole 2048-element batches
+    int64_t k;          // batches per block (the last block may own fewer)
+    int64_t rest0;      // first element of the ragged tail (= full * 2048)
+    int64_t rest_iters; // 512-element iterations of the tail (0..4, the last may be ragged)
+    int grid;           // blocks == records
+    // interleaved mode (large tensors): block b owns the 4-batch chunks b, b + grid, b + 2 grid, ...
+    // so the resident blocks sweep the tensor as ONE moving band of addresses (DRAM-page friendly,
+    // like the dynamically scheduled streaming kernel) instead of `grid` far-apart streams
+    int interleave;
+    int64_t chunks;     // ceil(full / 4)
 };
-__host__ __device__ inline FlatGeom make_flat_geom(int64_t n, int cap) {
+// Batch-granular balance: k = ceil(full / cap) batches per block, grid = ceil(full / k) blocks, so
+// every block but the last owns exactly k batches.  (Balancing the remainder at 512-element
+// granularity through a separate direct-load path was measured and rejected: the extra
+// un-pipelined phase per block cost more than the evened-out batch bought,
+// profiles/r02_midsize.md.)
+__host__ __device__ inline FlatGeom make_flat_geom(int64_t n, int cap, int interleave = 0) {
     FlatGeom f;
     f.n = n;
-    f.full = n / kBatchElems;
     if (cap > kFlatCapMax) cap = kFlatCapMax;
     if (cap < 1) cap = 1;
-    int64_t k = (f.full + cap - 1) / cap;
-    if (k < 1) k = 1;
-    f.per_cta = k;
-    int64_t gsz = (f.full + k - 1) / k;
-    if (gsz < 1) gsz = 1;
-    f.grid = (int)gsz;
+    f.full = n / kBatchElems;
+    f.interleave = interleave;
+    f.chunks = (f.full + kFlatGroup - 1) / kFlatGroup;
+    if (interleave) {
+        int64_t kc = (f.chunks + cap - 1) / cap;          // chunks per block
+        if (kc < 1) kc = 1;
+        int64_t gsz = (f.chunks + kc - 1) / kc;
+        if (gsz < 1) gsz = 1;
+        f.grid = (int)gsz;
+        f.k = kc * kFlatGroup;                            // upper bound of batches per block
+    } else {
+        f.k = (f.full + cap - 1) / cap;
+        if (f.k < 1) f.k = 1;
+        int64_t gsz = (f.full + f.k - 1) / f.k;
+        if (gsz < 1) gsz = 1;
+        f.grid = (int)gsz;
+    }
+    f.rest0 = f.full * kBatchElems;
+    f.rest_iters = (n - f.rest0 + kIterElems - 1) / kIterElems;
     return f;
 }
 
@@ -822,21 +846,109 @@ __device__ __forceinline__ void flat_fold(Acc &acc, Acc2 &a2, double (*s_acc)[kT
     a2 = {0ull, 0ull, 0ull};
 }
 
+// ---- TMA (bulk async copy) + mbarrier helpers: global -> shared staging of the operands ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// 1-D bulk copy global -> shared; completion (bytes landed) is signalled on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+constexpr int kFlatStages = 2;     // operand staging ring: 2 x (8 KB x + 8 KB go) per CTA
+
 template <int METHOD, bool CLAMP, int NOISE>
 __global__ void __launch_bounds__(kThreads, MHAQ_BWD_MIN_CTAS)
 fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, float *__restrict__ gx,
                    QParams prm, FlatGeom f, const float *__restrict__ r, uint64_t seed,
                    uint64_t offset, const uint64_t *__restrict__ philox_dev, double *__restrict__ ws,
                    unsigned int *ticket, float *__restrict__ o0, float *__restrict__ o1,
-                   float *__restrict__ o2, float *__restrict__ o3) {
+                   float *__restrict__ o2, float *__restrict__ o3, int exp_flags) {
     static_assert(METHOD == MHAQ_FQ_STE || METHOD == MHAQ_FQ_LSQ, "flat backward: STE / LSQ only");
     const int tid = threadIdx.x;
+    // Operands arrive through the TMA engine (cp.async.bulk, 8 KB per operand per batch) into a
+    // 2-stage shared-memory ring guarded by mbarriers: the copy of batch i+1 is in flight while
+    // batch i is computed, whatever the register budget — a short kernel has no steady state in
+    // which resident CTAs would drift apart and overlap each other's load and compute phases.
+    __shared__ __align__(128) float s_x[kFlatStages][kBatchElems];
+    __shared__ __align__(128) float s_g[kFlatStages][kBatchElems];
+    __shared__ __align__(8) uint64_t s_bar[kFlatStages];
     __shared__ double s_acc[5][kThreads / 32];
     __shared__ double s_fin[5][kFinThreads / 32];
     __shared__ int s_last;
+    constexpr uint32_t kOpBytes = kBatchElems * sizeof(float);   // 8192
+    const int64_t b0 = (int64_t)blockIdx.x * f.k;
+    int nb;                                                       // batches of this block
+    if (f.interleave) {
+        const int64_t mine = f.chunks > blockIdx.x ? (f.chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        nb = (int)(mine * kFlatGroup);
+        // the tensor's last chunk may be short; it belongs to block (chunks - 1) % grid
+        if (mine > 0 && (f.chunks - 1) % gridDim.x == blockIdx.x) nb -= (int)(f.chunks * kFlatGroup - f.full);
+    } else {
+        nb = (int)(f.full - b0 < f.k ? (f.full > b0 ? f.full - b0 : 0) : f.k);
+    }
+    // i-th batch of this block -> batch index in the tensor
+    auto batch_of = [&](int i) -> int64_t {
+        if (!f.interleave) return b0 + i;
+        return ((int64_t)(i / kFlatGroup) * gridDim.x + blockIdx.x) * kFlatGroup + (i % kFlatGroup);
+    };
+    // first thing: get the first two batches moving (nothing below is needed to issue them)
+    if (tid == 0 && nb > 0) {
+#pragma unroll
+        for (int s = 0; s < kFlatStages; ++s) mbar_init(&s_bar[s], 1);
+        mbar_fence_init();
+        for (int s = 0; s < kFlatStages && s < nb; ++s) {
+            const int64_t Bs = batch_of(s);
+            mbar_expect_tx(&s_bar[s], 2 * kOpBytes);
+            bulk_g2s(s_x[s], x + Bs * kBatchElems, kOpBytes, &s_bar[s]);
+            bulk_g2s(s_g[s], go + Bs * kBatchElems, kOpBytes, &s_bar[s]);
+        }
+    }
     if ((tid & 31) == 0) {
 #pragma unroll
         for (int m = 0; m < 5; ++m) s_acc[m][tid >> 5] = 0.0;
+    }
+    // the ragged tail (< one batch, up to 4 iterations) belongs to the last block: its loads are
+    // in flight next to the TMA copies
+    const bool owns_tail = (blockIdx.x == gridDim.x - 1) && f.rest_iters > 0;
+    const int64_t r_it0 = owns_tail ? 0 : f.rest_iters;
+    float4 rx[4], rg[4], rr4[4];
+    bool rvalid[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int64_t it = r_it0 + u;
+        const int64_t p = f.rest0 + it * kIterElems + tid * 4;
+        rvalid[u] = (it < f.rest_iters) && (p < f.n);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        rx[u] = rvalid[u] ? ld_stream4(x + p) : z;
+        rg[u] = rvalid[u] ? ld_stream4(go + p) : z;
+        rr4[u] = (NOISE == NOISE_EXPLICIT && rvalid[u]) ? ld_stream4(r + p) : z;
     }
     PhiloxKey key = {0, 0, 0, 0};
     if (NOISE == NOISE_PHILOX) key = make_key(seed, offset, philox_dev);
@@ -860,40 +972,81 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
     int64_t curT = -1;
     int in_group = 0;
 
-    const int64_t b0 = (int64_t)blockIdx.x * f.per_cta;
-    int64_t b1 = b0 + f.per_cta;
-    if (b1 > f.full) b1 = f.full;
-    // the ragged tail (< one batch) belongs to the last block
-    const bool tail = (blockIdx.x == gridDim.x - 1) && (f.full * kBatchElems < f.n);
-    const int64_t b_end = tail ? f.full + 1 : b1;
+    // ---- ragged tail: up to 4 single iterations (the element position decides the noise) ----
+    {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!rvalid[u]) continue;
+            const int64_t p = f.rest0 + (r_it0 + u) * kIterElems + tid * 4;
+            const int64_t git = (f.rest0 >> 9) + r_it0 + u;          // global iteration index (512 elements)
+            uint32_t inv = 0;
+            if (NOISE == NOISE_PHILOX) {
+                const int64_t T = git >> 5;                          // 32 iterations per super-tile
+                if (T != curT) {
+                    rnd = noise_block(key, 0, supers_per_row, T, tid);
+                    curT = T;
+                }
+                inv = ~noise_nibble(rnd, (int)(git & 31));
+            }
+            float4 o;
+            // (smallest non-zero |go| >= 2^-56, else the exact IEEE division: same guard as a batch)
+            const bool odd = nzmin4(0xffffffffu, rg[u]) < kGoLoBits2m1;
+            if (fast_ok && !odd) {
+                bwd_pair_fast<METHOD, CLAMP, NOISE>(rx[u].x, rx[u].y, rg[u].x, rg[u].y, rr4[u].x, rr4[u].y,
+                                                    inv << 31, inv << 30, q, pc, a2, acc, o.x, o.y);
+                bwd_pair_fast<METHOD, CLAMP, NOISE>(rx[u].z, rx[u].w, rg[u].z, rg[u].w, rr4[u].z, rr4[u].w,
+                                                    inv << 29, inv << 28, q, pc, a2, acc, o.z, o.w);
+            } else {
+                o.x = bwd_elem<METHOD, CLAMP, NOISE, false, false>(rx[u].x, rg[u].x, rr4[u].x, inv << 31, q, bc, acc);
+                o.y = bwd_elem<METHOD, CLAMP, NOISE, false, false>(rx[u].y, rg[u].y, rr4[u].y, inv << 30, q, bc, acc);
+                o.z = bwd_elem<METHOD, CLAMP, NOISE, false, false>(rx[u].z, rg[u].z, rr4[u].z, inv << 29, q, bc, acc);
+                o.w = bwd_elem<METHOD, CLAMP, NOISE, false, false>(rx[u].w, rg[u].w, rr4[u].w, inv << 28, q, bc, acc);
+            }
+            if (gx) st_stream4(gx + p, o);
+        }
+        // BLOCK-uniform (never per-thread: the fold below runs full-mask warp shuffles)
+        if (owns_tail) ++in_group;
+    }
 
-    for (int64_t B = b0; B < b_end; ++B) {
-        const bool is_tail = B >= b1;                        // only possible for the last block
-        const int64_t Bq = is_tail ? f.full : B;
-        const int64_t base = Bq * kBatchElems + tid * 4;
-        const int it0 = (int)(Bq & 7) * kU;                  // iteration index inside the super-tile
+    // ---- main region: nb aligned batches through the TMA ring ----
+    if (nb > 0) __syncthreads();                                 // the mbarriers are initialised
+    for (int i = 0; i < nb; ++i) {
+        const int64_t B = batch_of(i);
+        const int st = i % kFlatStages;
+        const int64_t base = B * kBatchElems + tid * 4;
+        const int it0 = (int)(B & 7) * kU;                       // iteration index inside the super-tile
+        uint32_t nw = 0;
         if (NOISE == NOISE_PHILOX) {
-            const int64_t T = Bq >> 3;                       // 8 batches per 16384-element super-tile
+            const int64_t T = B >> 3;                            // 8 batches per 16384-element super-tile
             if (T != curT) {
                 rnd = noise_block(key, 0, supers_per_row, T, tid);
                 curT = T;
             }
+            const int wi = it0 >> 3;                             // 32-bit word of the 128-bit block
+            nw = ~((wi < 2) ? ((wi == 0) ? rnd.x : rnd.y) : ((wi == 2) ? rnd.z : rnd.w));
+            if (it0 & 4) nw >>= 16;                              // second half of the word's 8 iterations
         }
-        if (fast_ok && !is_tail) {
-            uint32_t nw = 0;
-            if (NOISE == NOISE_PHILOX) {
-                const int wi = it0 >> 3;                     // 32-bit word of the 128-bit block
-                nw = ~((wi < 2) ? ((wi == 0) ? rnd.x : rnd.y) : ((wi == 2) ? rnd.z : rnd.w));
-                if (it0 & 4) nw >>= 16;                      // second half of the word's 8 iterations
-            }
-            float4 xv[kU], gv[kU], rv4[kU];
+        mbar_wait(&s_bar[st], (uint32_t)(i / kFlatStages) & 1u);
+        float4 xv[kU], gv[kU], rv4[kU];
 #pragma unroll
-            for (int u = 0; u < kU; ++u) {
-                const int64_t p = base + u * kIterElems;
-                xv[u] = ld_stream4(x + p);
-                gv[u] = ld_stream4(go + p);
-                rv4[u] = (NOISE == NOISE_EXPLICIT) ? ld_stream4(r + p) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int u = 0; u < kU; ++u) {
+            xv[u] = *reinterpret_cast<const float4 *>(&s_x[st][u * kIterElems + tid * 4]);
+            gv[u] = *reinterpret_cast<const float4 *>(&s_g[st][u * kIterElems + tid * 4]);
+            rv4[u] = (NOISE == NOISE_EXPLICIT) ? ld_stream4(r + base + u * kIterElems)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // every thread is past the compute of batch i-1 here: its stage can be refilled (the
+        // refill of a stage is issued one full iteration after its last shared-memory read,
+        // never right behind it)
+        __syncthreads();
+        if (tid == 0 && i >= 1 && i + 1 < nb) {
+            const int sn = (i + 1) % kFlatStages;
+            const int64_t Bn = batch_of(i + 1);
+            mbar_expect_tx(&s_bar[sn], 2 * kOpBytes);
+            bulk_g2s(s_x[sn], x + Bn * kBatchElems, kOpBytes, &s_bar[sn]);
+            bulk_g2s(s_g[sn], go + Bn * kBatchElems, kOpBytes, &s_bar[sn]);
+        }
+        if (fast_ok) {
             uint32_t mn = 0xffffffffu;
 #pragma unroll
             for (int u = 0; u < kU; ++u) mn = nzmin4(mn, gv[u]);
@@ -913,17 +1066,16 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
             if (odd && gx)   // rare: exact IEEE division for the input gradient
                 fix_batch_exact<METHOD, CLAMP>(x, go, gx, base, q, bc.smul, bc.delta);
         } else {
-            // general path: true IEEE division (out-of-range scale, lo >= hi) and the ragged tail
+            // out-of-range scale / lo >= hi: true IEEE division on the staged operands
 #pragma unroll 1
             for (int u = 0; u < kU; ++u) {
                 const int64_t p = base + (int64_t)u * kIterElems;
-                const int nv = is_tail ? valid4<true>(p, f.n) : 4;
-                if (!nv) continue;
-                const float4 xe = ld_stream4(x + p), ge = ld_stream4(go + p);
-                float4 re = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (NOISE == NOISE_EXPLICIT) re = ld_stream4(r + p);
                 uint32_t inv = 0;
                 if (NOISE == NOISE_PHILOX) inv = ~noise_nibble(rnd, it0 + u);
+                const float4 xe = *reinterpret_cast<const float4 *>(&s_x[st][u * kIterElems + tid * 4]);
+                const float4 ge = *reinterpret_cast<const float4 *>(&s_g[st][u * kIterElems + tid * 4]);
+                float4 re = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (NOISE == NOISE_EXPLICIT) re = ld_stream4(r + p);
                 float4 o;
                 o.x = bwd_elem<METHOD, CLAMP, NOISE, false, false>(xe.x, ge.x, re.x, inv << 31, q, bc, acc);
                 o.y = bwd_elem<METHOD, CLAMP, NOISE, false, false>(xe.y, ge.y, re.y, inv << 30, q, bc, acc);
@@ -938,6 +1090,9 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
         }
     }
     if (in_group) flat_fold<CLAMP>(acc, a2, s_acc);
+    // (exp_flags: timing experiments only — MHAQ_FQ_FLAT_EXP=1 skips the reduction epilogue, the
+    // parameter gradients are then NOT produced; never set in production)
+    if (exp_flags & 1) return;
     __syncthreads();
     if (tid == 0) {
         double *rec = ws + (int64_t)blockIdx.x * kNPart;
@@ -1209,6 +1364,7 @@ fq_rowstat_bwd_kernel(const float *__restrict__ gx, const float *__restrict__ x,
 }
 
 #include "fq_wrow.cuh"
+#include "fq_loss.cuh"
 
 // ===========================================================================
 // Host-side launch helpers
@@ -1330,10 +1486,24 @@ inline int64_t flat_max_elems() {
     static int64_t mx = -1;
     if (mx < 0) {
         const char *e = getenv("MHAQ_FQ_FLAT_MAX_LOG2");
-        const int l2 = e ? atoi(e) : 26;
+        const int l2 = e ? atoi(e) : 25;
         mx = l2 <= 0 ? 0 : (int64_t)1 << l2;
     }
     return mx;
+}
+// Tensors of at least this many elements use the interleaved (moving band) partition.
+inline int64_t flat_interleave_min() {
+    static int64_t mn = -1;
+    if (mn < 0) {
+        const char *e = getenv("MHAQ_FQ_FLAT_INTERLEAVE_LOG2");
+        const int l2 = e ? atoi(e) : 62;
+        mn = (int64_t)1 << (l2 < 0 ? 0 : (l2 > 62 ? 62 : l2));
+    }
+    return mn;
+}
+inline int flat_exp_flags() {
+    static const int v = env_int("MHAQ_FQ_FLAT_EXP");
+    return v;
 }
 inline bool flat_shape_ok(int64_t n_rows, int64_t n_inner, int64_t n_ch, int method, int codegrad) {
     return n_rows == 1 && n_ch == 1 && !codegrad && (n_inner % 4 == 0) && n_inner <= flat_max_elems() &&
@@ -1347,7 +1517,7 @@ int launch_bwd_flat(bool explicit_r, const FlatGeom &f, cudaStream_t st, const f
                     float *o2, float *o3) {
 #define MHAQ_FLAT(N)                                                                              \
     fq_bwd_flat_kernel<METHOD, CLAMP, N><<<f.grid, kThreads, 0, st>>>(                            \
-        go, x, gx, prm, f, r, seed, offset, philox_dev, ws, ticket, o0, o1, o2, o3)
+        go, x, gx, prm, f, r, seed, offset, philox_dev, ws, ticket, o0, o1, o2, o3, flat_exp_flags())
     if (METHOD == MHAQ_FQ_LSQ) MHAQ_FLAT(NOISE_NONE);
     else if (explicit_r) MHAQ_FLAT(NOISE_EXPLICIT);
     else MHAQ_FLAT(NOISE_PHILOX);
@@ -1523,7 +1693,7 @@ int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx, const floa
             !stride_ok(hi_stride))
             return MHAQ_FQ_EINVAL;
         const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode};
-        const FlatGeom f = make_flat_geom(n_inner, flat_cap());
+        const FlatGeom f = make_flat_geom(n_inner, flat_cap(), n_inner >= flat_interleave_min());
         const bool clamp = has_clamp(param_mode, lo, hi);
         cudaStream_t st = (cudaStream_t)stream;
         const bool er = (r != nullptr);
@@ -1643,6 +1813,111 @@ int mhaq_fq_wrow_bwd_f32(const float *g_wq, const float *w, const float *log_sca
         return r ? MHAQ_WROW(MHAQ_FQ_STE, NOISE_EXPLICIT) : MHAQ_WROW(MHAQ_FQ_STE, NOISE_PHILOX);
     return r ? MHAQ_WROW(MHAQ_FQ_EWGS, NOISE_EXPLICIT) : MHAQ_WROW(MHAQ_FQ_EWGS, NOISE_PHILOX);
 #undef MHAQ_WROW
+}
+
+int mhaq_fq_wrow_multi_fwd_f32(const mhaq_fq_wrow_fwd_desc *descs, int n_tensors, void *stream) {
+    if (n_tensors < 0) return MHAQ_FQ_EINVAL;
+    if (n_tensors == 0) return 0;
+    if (!descs) return MHAQ_FQ_ENULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int c0 = 0; c0 < n_tensors; c0 += kWRowMultiMax) {
+        WRowFwdMulti m;
+        m.n = 0;
+        m.row0[0] = 0;
+        for (int i = c0; i < n_tensors && m.n < kWRowMultiMax; ++i) {
+            const mhaq_fq_wrow_fwd_desc &d = descs[i];
+            if (!d.w || !d.log_scale) return MHAQ_FQ_ENULL;
+            if (d.n_rows < 0 || d.n_inner <= 0 || d.n_rows > 0x3fffffff) return MHAQ_FQ_EINVAL;
+            if (d.n_rows == 0) continue;
+            const int k = m.n++;
+            m.d[k] = {d.w, d.log_scale, d.wq, d.row_min, d.row_max, d.log_range, d.n_inner};
+            m.vec[k] = (d.n_inner % 4 == 0) && aligned16(d.w) && (!d.wq || aligned16(d.wq));
+            m.row0[k + 1] = m.row0[k] + (int)d.n_rows;
+        }
+        if (m.n == 0) continue;
+        fq_wrow_multi_fwd_kernel<<<grid_for(m.row0[m.n]), kThreads, 0, st>>>(m);
+        const int rc = last_error();
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int mhaq_fq_wrow_multi_bwd_f32(const mhaq_fq_wrow_bwd_desc *descs, int n_tensors, int method,
+                               uint64_t seed, uint64_t offset, const uint64_t *philox_dev, void *stream) {
+    if (n_tensors < 0) return MHAQ_FQ_EINVAL;
+    if (n_tensors == 0) return 0;
+    if (!descs) return MHAQ_FQ_ENULL;
+    if (method != MHAQ_FQ_STE && method != MHAQ_FQ_EWGS && method != MHAQ_FQ_LSQ) return MHAQ_FQ_EINVAL;
+    bool explicit_r = false;
+    for (int i = 0; i < n_tensors; ++i) {
+        const mhaq_fq_wrow_bwd_desc &d = descs[i];
+        if (!d.g_wq || !d.w || !d.log_scale || !d.row_min || !d.row_max) return MHAQ_FQ_ENULL;
+        if (d.n_rows < 0 || d.n_inner <= 0 || d.n_rows > 0x3fffffff) return MHAQ_FQ_EINVAL;
+        if (i == 0) explicit_r = d.r != nullptr;
+        else if ((d.r != nullptr) != explicit_r) return MHAQ_FQ_EINVAL;   // all explicit or all in-kernel
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int c0 = 0; c0 < n_tensors; c0 += kWRowMultiBwdMax) {
+        WRowBwdMulti m;
+        m.n = 0;
+        m.row0[0] = 0;
+        // (every tensor of the chunk keeps a slot, empty ones included: slot index == noise stream index)
+        for (int i = c0; i < n_tensors && m.n < kWRowMultiBwdMax; ++i) {
+            const mhaq_fq_wrow_bwd_desc &d = descs[i];
+            const int k = m.n++;
+            m.d[k] = {d.g_wq, d.w, d.log_scale, d.row_min, d.row_max, d.g_log_range, d.g_row_min,
+                      d.g_row_max, d.r, d.g_w, d.g_log_scale, d.n_inner};
+            m.vec[k] = (d.n_inner % 4 == 0) && aligned16(d.w) && aligned16(d.g_wq) &&
+                       (!d.g_w || aligned16(d.g_w)) && (!d.r || aligned16(d.r));
+            m.row0[k + 1] = m.row0[k] + (int)d.n_rows;
+        }
+        if (m.row0[m.n] == 0) continue;
+        const int grid = grid_for(m.row0[m.n]);
+        const uint64_t off = offset + (uint64_t)c0;
+#define MHAQ_WMULTI(M, N) fq_wrow_multi_bwd_kernel<M, N><<<grid, kThreads, 0, st>>>(m, seed, off, philox_dev)
+        if (method == MHAQ_FQ_LSQ) MHAQ_WMULTI(MHAQ_FQ_LSQ, NOISE_NONE);
+        else if (method == MHAQ_FQ_STE) {
+            if (explicit_r) MHAQ_WMULTI(MHAQ_FQ_STE, NOISE_EXPLICIT); else MHAQ_WMULTI(MHAQ_FQ_STE, NOISE_PHILOX);
+        } else {
+            if (explicit_r) MHAQ_WMULTI(MHAQ_FQ_EWGS, NOISE_EXPLICIT); else MHAQ_WMULTI(MHAQ_FQ_EWGS, NOISE_PHILOX);
+        }
+#undef MHAQ_WMULTI
+        const int rc = last_error();
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int mhaq_fq_potential_loss_fwd_f32(const float *log_act_s, const float *log_act_q, int64_t n_act,
+                                   const float *log_wght_s, const float *log_w_range, int64_t n_wght,
+                                   const float *base_loss, float *loss_sum, float *cnt, float w_target,
+                                   float a_target, float eps, float t, int lossless, int training,
+                                   float *out, void *stream) {
+    if (!log_act_s || !log_act_q || !log_wght_s || !log_w_range || !base_loss || !loss_sum || !cnt || !out)
+        return MHAQ_FQ_ENULL;
+    if (n_act < 0 || n_wght < 0) return MHAQ_FQ_EINVAL;
+    const PLossArgs a = {log_act_s, log_act_q, log_wght_s, log_w_range, n_act, n_wght,
+                         w_target, a_target, eps, t, lossless, training};
+    fq_potential_loss_fwd_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>(a, base_loss, loss_sum, cnt, out);
+    return last_error();
+}
+
+int mhaq_fq_potential_loss_bwd_f32(const float *log_act_s, const float *log_act_q, int64_t n_act,
+                                   const float *log_wght_s, const float *log_w_range, int64_t n_wght,
+                                   const float *saved, const float *g_loss, float w_target, float a_target,
+                                   float eps, float *g_log_act_s, float *g_log_act_q, float *g_log_wght_s,
+                                   float *g_log_w_range, float *g_base_loss, void *stream) {
+    if (!log_act_s || !log_act_q || !log_wght_s || !log_w_range || !saved || !g_loss) return MHAQ_FQ_ENULL;
+    if (n_act < 0 || n_wght < 0) return MHAQ_FQ_EINVAL;
+    const PLossArgs a = {log_act_s, log_act_q, log_wght_s, log_w_range, n_act, n_wght,
+                         w_target, a_target, eps, 0.f, 0, 0};
+    const int64_t n = n_wght > n_act ? n_wght : n_act;
+    int grid = (int)((n + kLossThreads - 1) / kLossThreads);
+    if (grid < 1) grid = 1;
+    if (grid > 1024) grid = 1024;
+    fq_potential_loss_bwd_kernel<<<grid, kLossThreads, 0, (cudaStream_t)stream>>>(
+        a, saved, g_loss, g_log_act_s, g_log_act_q, g_log_wght_s, g_log_w_range, g_base_loss);
+    return last_error();
 }
 
 int mhaq_fq_noise_f32(float *r, int64_t n_rows, int64_t n_inner, uint64_t seed, uint64_t offset,

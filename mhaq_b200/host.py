@@ -35,6 +35,12 @@ def fake_quant_fwd_bwd_host(x_host: torch.Tensor, go_host: torch.Tensor, scale, 
     as CUDA tensors shaped like the parameters.  The call returns after all device work has
     been enqueued and the output copies issued; synchronise before reading the host outputs."""
     device = torch.device(device) if device is not None else scale.device
+    if ops._method_id(method) == ops.METHOD_IDS["AEWGS"]:
+        # AEWGS needs whole-tensor (per-channel) statistics — all-reduced under DDP — BEFORE any
+        # chunk's backward can run: it cannot be streamed chunk by chunk.  Fail before any copy.
+        raise NotImplementedError("fake_quant_fwd_bwd_host streams the tensor in chunks; the AEWGS estimator "
+                                  "needs its per-channel statistics over the whole tensor first — use "
+                                  "mhaq_b200.fake_quant on a device-resident tensor")
     assert x_host.shape == go_host.shape and x_host.dtype == torch.float32
     if not (x_host.is_pinned() and go_host.is_pinned()):
         raise RuntimeError("fake_quant_fwd_bwd_host needs pinned host tensors")

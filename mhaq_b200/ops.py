@@ -848,3 +848,160 @@ def weight_fake_quant_rows(w, log_wght_s, method="STE", noise=None, philox=None)
         raise RuntimeError("weight_fake_quant_rows: needs one log-scale per row of dim 0, rows of at "
                            f"most {WROW_MAX_INNER} elements and a method other than AEWGS")
     return _WeightRowFn.apply(w, log_wght_s, _method_id(method), noise, philox)
+
+
+# ---------------------------------------------------------------------------------------------
+# Multi-tensor row-resident weight path (include/mhaq_fq.h: mhaq_fq_wrow_multi_*): every
+# per-channel weight of a model in ONE launch forward and ONE backward.
+# ---------------------------------------------------------------------------------------------
+def _philox_streams(x, method: int, n: int, philox):
+    """(seed, base offset, device state) for `n` consecutive noise streams."""
+    if method == METHOD_IDS["LSQ"]:
+        return 0, 0, None
+    if philox is not None:
+        return philox[0], philox[1], None
+    pd = _philox_dev.get(x.device.index)
+    if pd is not None:
+        off = _philox_call[x.device.index]
+        _philox_call[x.device.index] = off + n
+        return 0, off, pd
+    idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    gen = torch.cuda.default_generators[idx]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(off + 4 * n)
+    return seed & 0xFFFFFFFFFFFFFFFF, off // 4, None
+
+
+class _WeightRowMultiFn(torch.autograd.Function):
+    """_WeightRowFn for n tensors at once: inputs (w_0..w_{n-1}, log_s_0..log_s_{n-1}), outputs
+    (wq_i, row_min_i, row_max_i, log_range_i) for every i — 4n outputs of one autograd node whose
+    backward is one launch too (it runs once the last consumer of any output has run)."""
+
+    @staticmethod
+    def forward(ctx, method, noises, philox, n, *tensors):
+        from ._lib import WRowFwdDesc
+        ctx.set_materialize_grads(False)
+        ws = [_dense(w, 0) for w in tensors[:n]]
+        lss = [ls if ls.is_contiguous() else ls.contiguous() for ls in tensors[n:]]
+        rows = [w.shape[0] for w in ws]
+        dev = ws[0].device
+        stats = torch.empty(3, sum(rows), dtype=torch.float32, device=dev)
+        descs = (WRowFwdDesc * n)()
+        outs, r0 = [], 0
+        for i, (w, ls) in enumerate(zip(ws, lss)):
+            wq = torch.empty_like(w)
+            r1 = r0 + rows[i]
+            mn, mx, lr = stats[0, r0:r1], stats[1, r0:r1], stats[2, r0:r1]
+            d = descs[i]
+            d.w, d.log_scale, d.wq = w.data_ptr(), ls.data_ptr(), wq.data_ptr()
+            d.row_min, d.row_max, d.log_range = mn.data_ptr(), mx.data_ptr(), lr.data_ptr()
+            d.n_rows, d.n_inner = rows[i], w.numel() // rows[i]
+            outs += [wq, mn, mx, lr]
+            r0 = r1
+        check(lib.mhaq_fq_wrow_multi_fwd_f32(descs, n, _stream()), "mhaq_fq_wrow_multi_fwd_f32")
+        ctx.save_for_backward(*ws, *lss, stats)
+        ctx.n, ctx.rows, ctx.method, ctx.noises, ctx.philox = n, rows, method, noises, philox
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        from ._lib import WRowBwdDesc
+        n, rows = ctx.n, ctx.rows
+        saved = ctx.saved_tensors
+        ws, lss, stats = saved[:n], saved[n:2 * n], saved[2 * n]
+        need = ctx.needs_input_grad
+        descs = (WRowBwdDesc * n)()
+        keep, gws, glss = [], [], []
+        r0 = 0
+        c = lambda t: None if t is None else t.contiguous()
+        for i in range(n):
+            w, ls = ws[i], lss[i]
+            g_wq, g_mn, g_mx, g_lr = grads[4 * i: 4 * i + 4]
+            g_wq = torch.zeros_like(w) if g_wq is None else _like_layout(g_wq, w)
+            g_mn, g_mx, g_lr = c(g_mn), c(g_mx), c(g_lr)
+            noise = None if ctx.noises is None else ctx.noises[i]
+            if noise is not None:
+                noise = _like_layout(noise, w)
+            gw = torch.empty_like(w) if need[4 + i] else None
+            gls = torch.empty(rows[i], dtype=torch.float32, device=w.device) if need[4 + n + i] else None
+            r1 = r0 + rows[i]
+            d = descs[i]
+            d.g_wq, d.w, d.log_scale = g_wq.data_ptr(), w.data_ptr(), ls.data_ptr()
+            d.row_min, d.row_max = stats[0, r0:r1].data_ptr(), stats[1, r0:r1].data_ptr()
+            d.g_log_range, d.g_row_min, d.g_row_max, d.r = _ptr(g_lr), _ptr(g_mn), _ptr(g_mx), _ptr(noise)
+            d.g_w, d.g_log_scale = _ptr(gw), _ptr(gls)
+            d.n_rows, d.n_inner = rows[i], w.numel() // rows[i]
+            keep += [g_wq, g_mn, g_mx, g_lr, noise]
+            gws.append(gw)
+            glss.append(None if gls is None else gls.reshape(ls.shape))
+            r0 = r1
+        seed, offset, pdev = (0, 0, None) if ctx.noises is not None else _philox_streams(ws[0], ctx.method, n, ctx.philox)
+        check(lib.mhaq_fq_wrow_multi_bwd_f32(descs, n, ctx.method, seed, offset, _ptr(pdev), _stream()),
+              "mhaq_fq_wrow_multi_bwd_f32")
+        return (None, None, None, None, *gws, *glss)
+
+
+def weight_fake_quant_rows_multi(weights, log_scales, method="STE", noises=None, philox=None):
+    """[(wq, row_min, row_max, log_range), ...] for a list of per-channel weights with short rows
+    (each must satisfy `weight_rows_fusable`), one launch each way for the whole list."""
+    n = len(weights)
+    if n == 0:
+        return []
+    mid = _method_id(method)
+    for w, ls in zip(weights, log_scales):
+        _require_cuda(w)
+        if not weight_rows_fusable(w, ls, mid):
+            raise RuntimeError("weight_fake_quant_rows_multi: every tensor needs one log-scale per row of dim 0, "
+                               f"rows of at most {WROW_MAX_INNER} elements and a method other than AEWGS")
+    if mid == METHOD_IDS["LSQ"]:
+        noises = None
+    out = _WeightRowMultiFn.apply(mid, noises, philox, n, *weights, *log_scales)
+    return [tuple(out[4 * i: 4 * i + 4]) for i in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------
+# PotentialLoss's constraint arithmetic (include/mhaq_fq.h: mhaq_fq_potential_loss_*): one
+# launch forward, one backward, instead of ~30 tiny elementwise / reduction launches per step.
+# ---------------------------------------------------------------------------------------------
+PLOSS_NOUT = 14
+
+
+class _PotentialLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, base_loss, las, laq, lws, lwq, loss_sum, cnt, wt, at, eps, t, lossless, training):
+        c = lambda v: v if v.is_contiguous() else v.contiguous()
+        las, laq, lws, lwq = c(las), c(laq), c(lws), c(lwq)
+        out = torch.empty(PLOSS_NOUT, dtype=torch.float32, device=lws.device)
+        check(lib.mhaq_fq_potential_loss_fwd_f32(_ptr(las), _ptr(laq), las.numel(), _ptr(lws), _ptr(lwq),
+                                                 lws.numel(), _ptr(base_loss), _ptr(loss_sum), _ptr(cnt),
+                                                 float(wt), float(at), float(eps), float(t), int(lossless),
+                                                 int(training), _ptr(out), _stream()),
+              "mhaq_fq_potential_loss_fwd_f32")
+        ctx.save_for_backward(las, laq, lws, lwq, out)
+        ctx.cfg = (float(wt), float(at), float(eps))
+        ctx.mark_non_differentiable(out)
+        return out[0], out
+
+    @staticmethod
+    def backward(ctx, g, _g_out):
+        las, laq, lws, lwq, out = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        g = g.contiguous()
+        mk = lambda t, n: torch.empty_like(t) if n else None
+        g_base = torch.empty((), dtype=torch.float32, device=lws.device) if need[0] else None
+        g_las, g_laq, g_lws, g_lwq = mk(las, need[1]), mk(laq, need[2]), mk(lws, need[3]), mk(lwq, need[4])
+        wt, at, eps = ctx.cfg
+        check(lib.mhaq_fq_potential_loss_bwd_f32(_ptr(las), _ptr(laq), las.numel(), _ptr(lws), _ptr(lwq),
+                                                 lws.numel(), _ptr(out), _ptr(g), wt, at, eps, _ptr(g_las),
+                                                 _ptr(g_laq), _ptr(g_lws), _ptr(g_lwq), _ptr(g_base), _stream()),
+              "mhaq_fq_potential_loss_bwd_f32")
+        return (g_base, g_las, g_laq, g_lws, g_lwq) + (None,) * 8
+
+
+def potential_loss(base_loss, las, laq, lws, lwq, loss_sum, cnt, wt, at, eps, t, lossless, training):
+    """(ploss, record) — see include/mhaq_fq.h; `loss_sum` / `cnt` are 1-element fp32 CUDA tensors
+    updated in place when `training`.  `record` holds the logged terms (non-differentiable)."""
+    for v in (base_loss, las, laq, lws, lwq, loss_sum, cnt):
+        _require_cuda(v)
+    return _PotentialLossFn.apply(base_loss.reshape(()), las, laq, lws, lwq, loss_sum, cnt, wt, at, eps, t,
+                                  lossless, training)

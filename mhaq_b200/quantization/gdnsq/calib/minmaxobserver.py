@@ -60,9 +60,12 @@ def apply_mean_stats_activations(module, abits=8, max_bits=24):
                     (m, "log_act_q", log_s + abits, m.log_act_q.requires_grad),
                     (m, "log_act_s", log_s, m.log_act_s.requires_grad))
         else:                                      # zero-width input: pruned, frozen
-            vals = ((m, "log_act_q", 0.0, False), (m, "log_act_s", 0.0, False), (m, "act_b", mn, False))
+            # (reference quirk kept: `torch.tensor([0])` makes these two INTEGER parameters,
+            # minmaxobserver.py:63-64 — exp2 of them is 1.0 either way)
+            vals = ((m, "log_act_q", 0, False), (m, "log_act_s", 0, False), (m, "act_b", mn, False))
         for mod, name, v, rg in vals:
-            setattr(mod, name, torch.nn.Parameter(torch.tensor([float(v)], device=dev), requires_grad=rg))
+            t = torch.tensor([v], device=dev) if isinstance(v, int) else torch.tensor([float(v)], device=dev)
+            setattr(mod, name, torch.nn.Parameter(t, requires_grad=rg))
 
 
 def apply_quantile_weights_s(module, wbits=8, max_bits=24, qscheme="per-channel"):

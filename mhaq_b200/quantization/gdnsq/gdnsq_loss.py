@@ -5,7 +5,9 @@ pair, ``PotentialLossNoPred`` with a precomputed base loss).
     ploss = calib_mul * l1 * (wmul*wloss + amul*aloss) + l2 * rloss
     wloss = mean(max(0, (log_w_range - log_wght_s) - (w_target - eps))^p)   (same for act)
 
-Row (f)-1 of SURVEY.md §8: host-side glue on O(#channels) tensors, plain PyTorch."""
+Row (f)-1 / (f)-4 of SURVEY.md §8.  On the GPU (fp32, p == 1) the whole expression and its autograd
+are one kernel each way (`mhaq_fq_potential_loss_fwd/bwd_f32`) instead of ~30 tiny ATen launches;
+otherwise the same operations in plain PyTorch."""
 import torch
 import torch.nn as nn
 
@@ -18,6 +20,7 @@ class _PotentialBase(nn.Module):
         self.s_act_loss = torch.tensor(0)
         self.weight_reg_loss = torch.tensor(0)
         self.p = torch.tensor(p)
+        self._p_int, self._eps = (int(p) if float(p) == int(p) else None), 1e-3   # host copies: no device sync per step
         self.at = a
         self.wt = w
         self.lossless = lossless
@@ -39,7 +42,32 @@ class _PotentialBase(nn.Module):
         self.p, self.l_eps, self.r_eps = (t.to(device) for t in (self.p, self.l_eps, self.r_eps))
         return self
 
+    def _fusable(self, base_loss, las, laq, lws, lwq):
+        """One kernel each way when everything lives on the GPU in fp32 and p == 1 (the only
+        exponent GDNSQQuant passes, gdnsq_quant.py:90-102)."""
+        return (self._p_int == 1 and not torch.is_tensor(self.t) and all(torch.is_tensor(v) and v.is_cuda and v.dtype == torch.float32
+                                         for v in (base_loss, las, laq, lws, lwq))
+                and las.numel() == laq.numel() and lws.numel() == lwq.numel())
+
+    def _combine_fused(self, base_loss, las, laq, lws, lwq):
+        from ... import ops
+        dev = lws.device
+        if not (torch.is_tensor(self.loss_sum) and self.loss_sum.is_cuda and torch.is_tensor(self.cnt)
+                and self.cnt.is_cuda):
+            # the running calibration state lives in device scalars from the first GPU step on
+            # (the reference's `loss_sum` becomes a device tensor at its first `+=` anyway)
+            self.loss_sum = torch.as_tensor(float(self.loss_sum), dtype=torch.float32, device=dev).reshape(1).clone()
+            self.cnt = torch.as_tensor(float(self.cnt), dtype=torch.float32, device=dev).reshape(1).clone()
+        self.base_loss = base_loss
+        ploss, rec = ops.potential_loss(base_loss, las, laq, lws, lwq, self.loss_sum, self.cnt, self.wt, self.at,
+                                        self._eps, float(self.t), self.lossless, self.training)
+        (self.wloss, self.aloss, self.rloss, self.s_weight_loss, self.q_weight_loss, self.s_act_loss,
+         self.q_act_loss, self.weight_reg_loss) = rec[1:9].unbind(0)
+        return ploss
+
     def _combine(self, base_loss, las, laq, lws, lwq):
+        if self._fusable(base_loss, las, laq, lws, lwq):
+            return self._combine_fused(base_loss, las, laq, lws, lwq)
         self.base_loss = base_loss
         z = torch.zeros((), dtype=torch.int64, device=lws.device)   # == torch.tensor(0), without a host copy
         wloss0 = torch.max(z, (lwq - lws) - (self.wt - self.l_eps)).pow(self.p)

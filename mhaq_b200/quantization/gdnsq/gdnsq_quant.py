@@ -27,7 +27,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ...aux.qutils import attrsetter, is_biased
-from ...aux.types import QScheme
+from ...aux.types import QScheme, scheme_id
 from ..abc.abc_quant import BaseQuant
 from .distill_losses import get_distillation_loss
 from .gdnsq_loss import PotentialLoss, PotentialLossNoPred
@@ -35,6 +35,7 @@ from .gdnsq_utils import QNMethod
 from .layers.gdnsq_act import NoisyAct
 from .layers.gdnsq_conv2d import NoisyConv2d
 from .layers.gdnsq_linear import NoisyLinear
+from .layers._multi import prequantize_weights
 from .utils.model_helper import ModelHelper
 
 _TRAIN_LOGS = (("Loss/Base train loss", "base_loss", True), ("Loss/Wloss", "wloss", False),
@@ -42,7 +43,8 @@ _TRAIN_LOGS = (("Loss/Base train loss", "base_loss", True), ("Loss/Wloss", "wlos
 
 
 def _as_qscheme(v):
-    return v if isinstance(v, QScheme) else QScheme(int(v))
+    """The YAML integer, the member name, this package's enum or the reference's own."""
+    return v if isinstance(v, QScheme) else QScheme(scheme_id(v))
 
 
 class GDNSQQuant(BaseQuant):
@@ -156,6 +158,7 @@ class GDNSQQuant(BaseQuant):
         self = train_step.__self__
 
         def wrapper(batch, batch_idx):
+            prequantize_weights(self.model)      # every conv weight in one launch (layers/_multi.py)
             outputs = (train_step(batch, batch_idx),
                        *ModelHelper.get_model_values(self.model, self.qscheme))
             loss = self.wrapped_criterion(outputs)
@@ -166,6 +169,7 @@ class GDNSQQuant(BaseQuant):
 
     @staticmethod
     def noisy_step(self, x):
+        prequantize_weights(self.model)          # every conv weight in one launch (layers/_multi.py)
         return (self.forward(x), *ModelHelper.get_model_values(self.model, self.qscheme))
 
     @staticmethod

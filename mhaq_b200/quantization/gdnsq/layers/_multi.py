@@ -1,0 +1,41 @@
+"""Model-wide weight fake-quantization: ONE launch forward, ONE backward for every per-channel
+conv weight of a model (reference: one `Q.dequantize(Q.quantize(w))` chain
+per layer per forward, gdnsq_conv2d.py:98, plus ModelHelper's range term per layer,
+model_helper.py:24-25,44).
+
+`prequantize_weights(model)` is called at the top of the patched training step.  It quantizes the
+weights of all eligible `NoisyConv2d` layers with `ops.weight_fake_quant_rows_multi` and installs
+the results as the layers' per-step cache entries, so each layer's `forward` (and
+`ModelHelper.get_model_values`) finds its quantized weight, row range and log-range term ready.
+Layers it cannot take (per-tensor, AEWGS, quantized bias, long rows, CPU) keep their own path; a
+model driven without this call (e.g. the reference's own GDNSQQuant on these layer classes) simply
+quantizes layer by layer.
+"""
+from __future__ import annotations
+
+import torch
+
+from .... import ops
+from .gdnsq_conv2d import NoisyConv2d
+
+
+def prequantize_weights(model: torch.nn.Module) -> int:
+    """Returns the number of layers served by the multi-tensor launch."""
+    if not torch.is_grad_enabled():
+        return 0                      # no_grad: the per-layer cache already survives across batches
+    groups = {}
+    for m in model.modules():
+        if isinstance(m, NoisyConv2d) and m.training and m.multi_ok():
+            key, hit = m.cache_probe()
+            if hit is None:
+                groups.setdefault((m.Q._method().value, m.weight.device), []).append((m, key))
+    served = 0
+    for (method, _dev), items in groups.items():
+        if len(items) < 2:
+            continue                  # a single layer gains nothing over its own launch
+        res = ops.weight_fake_quant_rows_multi([m.weight for m, _ in items],
+                                               [m.log_wght_s for m, _ in items], method=method)
+        for (m, key), (wq, mn, mx, lr) in zip(items, res):
+            m.adopt_quantized(key, wq, mn, mx, lr)
+        served += len(items)
+    return served

@@ -93,6 +93,26 @@ class NoisyConv2d(nn.Conv2d):
             self._wq_cache.store(key, out)
         return out
 
+    # ---- multi-tensor launch support (layers/_multi.py) --------------------------------------
+    def multi_ok(self) -> bool:
+        """May this layer's weight be quantized by the model-wide multi-tensor launch?"""
+        from .... import ops
+        return (is_per_channel(self.qscheme) and not self.quant_bias and self.positive_scale_ok()
+                and ops.weight_rows_fusable(self.weight, self.log_wght_s, self.Q._method()))
+
+    def cache_probe(self):
+        """(key, hit) of this step's weight-cache entry."""
+        return self._wq_cache.lookup((self.weight, self.log_wght_s, self.bias),
+                                     torch.is_grad_enabled(), self.training)
+
+    def adopt_quantized(self, key, wq, mn, mx, lr):
+        """Install (weight_q, row_min, row_max, log_range) computed by the multi-tensor launch as
+        this step's cache entry, exactly what `_quantize` would have stored."""
+        pshape = (self.weight.shape[0],) + (1,) * (self.weight.dim() - 1)
+        log_s, q = self.log_wght_s, self.Q
+        q.defer(lambda: (torch.exp2(log_s).reshape(pshape), mn.view(pshape), q._min_val, q._max_val))
+        self._wq_cache.store(key, (wq, self.bias, mn, mx, lr))
+
     def positive_scale_ok(self):
         return self.Q.positive_scale and self.weight.is_cuda
 

@@ -524,4 +524,24 @@ def test_noisy_linear_against_the_live_reference_fixture():
     assert_close_rel(x.grad, c["gx"], 1e-4, "gx", abs_floor=1e-5)
     assert_close_rel(lin.weight.grad, c["g_weight"], 1e-4, "g_weight", abs_floor=2e-5)
     assert_close_rel(lin.bias.grad, c["g_bias"], 1e-5, "g_bias", abs_floor=1e-6)
-    assert_close_rel(lin.log_wght_s.grad, c["g_log_wght_s"], 1e-3, "g_log_wght_s", abs_floor=1e-4)
+    # d/d log_wght_s by the parameter-gradient rule (oracle/checks.py): within 1e-5 of the live
+    # reference's fp32 value, or at least as close as it to the fp64 sum of the reference's own
+    # fp32 per-element terms.  The fixture was produced on the CPU: if CUDA's exp2f gives the
+    # scale a different last bit than the CPU's exp2 did, codes next to a rounding tie move and the
+    # comparison is not meaningful at 1e-5 — the on-device test against the live reference
+    # (tests/test_gpu_live_reference.py::test_noisy_linear_matches_the_live_reference_on_device)
+    # holds the tight bar in that case.
+    import math
+    from oracle.checks import assert_param_grad, exact_param_grads
+    ls_cpu = c["log_wght_s"].cpu()
+    same_scale = torch.equal(torch.exp2(ls_cpu), torch.exp2(ls_cpu.cuda()).cpu())
+    if same_scale:
+        w = c["weight"].cpu()
+        g_wq = c["go"].cpu().t() @ c["x"].cpu()
+        s = torch.exp2(ls_cpu)
+        ex = exact_param_grads(O.fake_quant, w, g_wq, s, w.amin().reshape(1), None, None, "LSQ", None)[0]
+        exact = ex.double() * s.double() * math.log(2.0)
+        assert_param_grad(lin.log_wght_s.grad, c["g_log_wght_s"], exact, 1e-5, "g_log_wght_s", 2e-6)
+    else:
+        assert_close_rel(lin.log_wght_s.grad, c["g_log_wght_s"], 1e-3, "g_log_wght_s (scale differs in the last bit)",
+                         abs_floor=1e-4)

@@ -103,6 +103,7 @@ def case(name, shape, per_channel, method="STE", clamp=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--large", action="store_true", help="per-tensor clamped STE at 12.8 M .. 2^28 elements only")
     ap.add_argument("--out", default=os.path.join("gpurun_out", "midsize.json"))
     a = ap.parse_args()
     rows = []
@@ -113,9 +114,12 @@ def main():
             ("rfdn act (4,12,256,256)", (4, 12, 256, 256))]
     if a.quick:
         acts = acts[2:6]
+    if a.large:
+        acts = [("resnet18 act (256,256,14,14)", (256, 256, 14, 14)), ("resnet18 act (256,128,28,28)", (256, 128, 28, 28)),
+                ("resnet18 act (256,64,56,56)", (256, 64, 56, 56)), ("2^26", (1 << 26,)), ("2^27", (1 << 27,)), ("2^28", (1 << 28,))]
     for nm, shp in acts:
         rows.append(case(nm, shp, False))
-    if not a.quick:
+    if not a.quick and not a.large:
         for log2n in (20, 22, 24, 26):
             for C in (0, 64, 512, 4096):
                 n = 1 << log2n
