@@ -164,10 +164,11 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets,
 
 /* mhaq_fq_bwd_f32 + mhaq_fq_bwd_finalize_f32 as one entry point (same arguments, the union of
  * the two lists).  For a per-tensor tensor (n_rows = n_ch = 1: every activation) with the
- * STE / LSQ estimator, gradient w.r.t. y and at most 2^25 elements it is ONE kernel: a
- * persistent, balanced grid (<= SMs x 5 blocks, each block one contiguous range) whose last
- * block to finish (ticket) sums the per-block fp64 records in index order and writes the
- * gradients — no second launch, no per-task flushes; bitwise reproducible on a given device.
+ * STE / LSQ estimator, gradient w.r.t. y and at most 2^28 elements it is ONE kernel: a
+ * persistent, balanced grid (<= SMs x 4 blocks; operands staged through a TMA bulk-copy ring;
+ * each block one contiguous range, or — from 2^24 elements — every grid-th 8 Ki-element chunk)
+ * whose last block to finish (ticket) sums the per-block fp64 records in index order and writes
+ * the gradients — no second launch, no per-task flushes; bitwise reproducible on a given device.
  * Everything else runs the two launches above.  mhaq_fq_bwd_single_launch() tells which (for
  * 16-byte aligned operands). */
 int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx,

@@ -881,10 +881,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "memory");
 }
 
-constexpr int kFlatStages = 2;     // operand staging ring: 2 x (8 KB x + 8 KB go) per CTA
+// operand staging ring: kFlatStages x (8 KB x + 8 KB go) per CTA (dynamic shared memory)
+#ifndef MHAQ_FLAT_STAGES
+#define MHAQ_FLAT_STAGES 2
+#endif
+constexpr int kFlatStages = MHAQ_FLAT_STAGES;
+// 4 compute warps + 1 auxiliary warp: the auxiliary warp's lane 0 drives the TMA ring and
+// publishes the block's record.  It never stores gradients, so its release fence before the
+// ticket has nothing to wait for — a compute thread's fence would sit out the L2 round trip of
+// the gradient stores it has just issued, on the critical path of the last block.
+constexpr int kFlatThreads = kThreads + 32;
+constexpr int kFlatSmemBytes = kFlatStages * 2 * kBatchElems * (int)sizeof(float);
+constexpr int kFlatCtasPerSm = 4;
 
 template <int METHOD, bool CLAMP, int NOISE>
-__global__ void __launch_bounds__(kThreads, MHAQ_BWD_MIN_CTAS)
+__global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm)
 fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, float *__restrict__ gx,
                    QParams prm, FlatGeom f, const float *__restrict__ r, uint64_t seed,
                    uint64_t offset, const uint64_t *__restrict__ philox_dev, double *__restrict__ ws,
@@ -892,12 +903,14 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
                    float *__restrict__ o2, float *__restrict__ o3, int exp_flags) {
     static_assert(METHOD == MHAQ_FQ_STE || METHOD == MHAQ_FQ_LSQ, "flat backward: STE / LSQ only");
     const int tid = threadIdx.x;
+    const bool aux = tid >= kThreads;                 // warp 4: TMA producer + record publisher
     // Operands arrive through the TMA engine (cp.async.bulk, 8 KB per operand per batch) into a
-    // 2-stage shared-memory ring guarded by mbarriers: the copy of batch i+1 is in flight while
+    // shared-memory ring guarded by mbarriers: the copies of the next batches are in flight while
     // batch i is computed, whatever the register budget — a short kernel has no steady state in
     // which resident CTAs would drift apart and overlap each other's load and compute phases.
-    __shared__ __align__(128) float s_x[kFlatStages][kBatchElems];
-    __shared__ __align__(128) float s_g[kFlatStages][kBatchElems];
+    extern __shared__ __align__(128) unsigned char flat_smem[];
+    float *const s_x = reinterpret_cast<float *>(flat_smem);                   // [stages][2048]
+    float *const s_g = s_x + kFlatStages * kBatchElems;                         // [stages][2048]
     __shared__ __align__(8) uint64_t s_bar[kFlatStages];
     __shared__ double s_acc[5][kThreads / 32];
     __shared__ double s_fin[5][kFinThreads / 32];
@@ -918,18 +931,30 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
         if (!f.interleave) return b0 + i;
         return ((int64_t)(i / kFlatGroup) * gridDim.x + blockIdx.x) * kFlatGroup + (i % kFlatGroup);
     };
-    // first thing: get the first two batches moving (nothing below is needed to issue them)
-    if (tid == 0 && nb > 0) {
+    // i-th batch of this block -> stage i % kFlatStages (armed with the byte count, then two copies)
+    auto issue = [&](int i) {
+        const int sg = i % kFlatStages;
+        const int64_t Bs = batch_of(i);
+        mbar_expect_tx(&s_bar[sg], 2 * kOpBytes);
+        bulk_g2s(s_x + sg * kBatchElems, x + Bs * kBatchElems, kOpBytes, &s_bar[sg]);
+        bulk_g2s(s_g + sg * kBatchElems, go + Bs * kBatchElems, kOpBytes, &s_bar[sg]);
+    };
+    if (aux) {
+        // ---- auxiliary warp: first thing, get the first batches moving; then refill a stage one
+        // full iteration after its last shared-memory read (every compute thread is past the
+        // compute of batch i-1 when it arrives at the barrier of iteration i)
+        if (tid == kThreads && nb > 0) {
 #pragma unroll
-        for (int s = 0; s < kFlatStages; ++s) mbar_init(&s_bar[s], 1);
-        mbar_fence_init();
-        for (int s = 0; s < kFlatStages && s < nb; ++s) {
-            const int64_t Bs = batch_of(s);
-            mbar_expect_tx(&s_bar[s], 2 * kOpBytes);
-            bulk_g2s(s_x[s], x + Bs * kBatchElems, kOpBytes, &s_bar[s]);
-            bulk_g2s(s_g[s], go + Bs * kBatchElems, kOpBytes, &s_bar[s]);
+            for (int sg = 0; sg < kFlatStages; ++sg) mbar_init(&s_bar[sg], 1);
+            mbar_fence_init();
+            for (int i = 0; i < kFlatStages && i < nb; ++i) issue(i);
         }
-    }
+        if (nb > 0) __syncthreads();                              // the mbarriers are initialised
+        for (int i = 0; i < nb; ++i) {
+            __syncthreads();
+            if (tid == kThreads && i >= 1 && i - 1 + kFlatStages < nb) issue(i - 1 + kFlatStages);
+        }
+    } else {
     if ((tid & 31) == 0) {
 #pragma unroll
         for (int m = 0; m < 5; ++m) s_acc[m][tid >> 5] = 0.0;
@@ -1030,22 +1055,14 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
         float4 xv[kU], gv[kU], rv4[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            xv[u] = *reinterpret_cast<const float4 *>(&s_x[st][u * kIterElems + tid * 4]);
-            gv[u] = *reinterpret_cast<const float4 *>(&s_g[st][u * kIterElems + tid * 4]);
+            xv[u] = *reinterpret_cast<const float4 *>(s_x + st * kBatchElems + u * kIterElems + tid * 4);
+            gv[u] = *reinterpret_cast<const float4 *>(s_g + st * kBatchElems + u * kIterElems + tid * 4);
             rv4[u] = (NOISE == NOISE_EXPLICIT) ? ld_stream4(r + base + u * kIterElems)
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        // every thread is past the compute of batch i-1 here: its stage can be refilled (the
-        // refill of a stage is issued one full iteration after its last shared-memory read,
-        // never right behind it)
+        // every thread is past the compute of batch i-1 here: the auxiliary warp refills that
+        // batch's stage behind this barrier
         __syncthreads();
-        if (tid == 0 && i >= 1 && i + 1 < nb) {
-            const int sn = (i + 1) % kFlatStages;
-            const int64_t Bn = batch_of(i + 1);
-            mbar_expect_tx(&s_bar[sn], 2 * kOpBytes);
-            bulk_g2s(s_x[sn], x + Bn * kBatchElems, kOpBytes, &s_bar[sn]);
-            bulk_g2s(s_g[sn], go + Bn * kBatchElems, kOpBytes, &s_bar[sn]);
-        }
         if (fast_ok) {
             uint32_t mn = 0xffffffffu;
 #pragma unroll
@@ -1072,8 +1089,8 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
                 const int64_t p = base + (int64_t)u * kIterElems;
                 uint32_t inv = 0;
                 if (NOISE == NOISE_PHILOX) inv = ~noise_nibble(rnd, it0 + u);
-                const float4 xe = *reinterpret_cast<const float4 *>(&s_x[st][u * kIterElems + tid * 4]);
-                const float4 ge = *reinterpret_cast<const float4 *>(&s_g[st][u * kIterElems + tid * 4]);
+                const float4 xe = *reinterpret_cast<const float4 *>(s_x + st * kBatchElems + u * kIterElems + tid * 4);
+                const float4 ge = *reinterpret_cast<const float4 *>(s_g + st * kBatchElems + u * kIterElems + tid * 4);
                 float4 re = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (NOISE == NOISE_EXPLICIT) re = ld_stream4(r + p);
                 float4 o;
@@ -1090,11 +1107,12 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
         }
     }
     if (in_group) flat_fold<CLAMP>(acc, a2, s_acc);
+    }   // compute warps
     // (exp_flags: timing experiments only — MHAQ_FQ_FLAT_EXP=1 skips the reduction epilogue, the
     // parameter gradients are then NOT produced; never set in production)
     if (exp_flags & 1) return;
     __syncthreads();
-    if (tid == 0) {
+    if (tid == kThreads) {
         double *rec = ws + (int64_t)blockIdx.x * kNPart;
 #pragma unroll
         for (int m = 0; m < 5; ++m) {
@@ -1110,7 +1128,7 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
     if (!s_last) return;
     __threadfence();
     double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int i = tid; i < (int)gridDim.x; i += kThreads) {
+    for (int i = tid; i < (int)gridDim.x; i += kFlatThreads) {
         const double *rec = ws + (int64_t)i * kNPart;
 #pragma unroll
         for (int m = 0; m < 5; ++m) a[m] += __ldcg(rec + m);
@@ -1474,19 +1492,21 @@ inline int flat_cap() {
         if (cudaGetDevice(&dev) != cudaSuccess ||
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
             sms = 148;
+        // 4 blocks per SM measured best (profiles/r02_midsize.md): 5 fit, but the fifth adds
+        // DRAM / L2 contention, not bandwidth
         const int per_sm = env_int("MHAQ_FQ_FLAT_CTAS_PER_SM");
-        cap = sms * (per_sm > 0 ? per_sm : MHAQ_BWD_MIN_CTAS);
+        cap = sms * (per_sm > 0 ? per_sm : kFlatCtasPerSm);
     }
     return cap;
 }
-// Largest tensor (elements) the flat backward takes; above it the dynamic one-CTA-per-task
-// streaming kernel + finalize launch wins (the hardware scheduler balances a long tail better than
-// a static partition).  MHAQ_FQ_FLAT_MAX_LOG2 overrides (0 disables the flat kernel).
+// Largest tensor (elements) the flat backward takes (2^28: with the interleaved partition it
+// matches or beats the dynamically scheduled streaming kernel + finalize launch up to there;
+// beyond, the streaming kernel stays).  MHAQ_FQ_FLAT_MAX_LOG2 overrides (0 disables the flat kernel).
 inline int64_t flat_max_elems() {
     static int64_t mx = -1;
     if (mx < 0) {
         const char *e = getenv("MHAQ_FQ_FLAT_MAX_LOG2");
-        const int l2 = e ? atoi(e) : 25;
+        const int l2 = e ? atoi(e) : 28;
         mx = l2 <= 0 ? 0 : (int64_t)1 << l2;
     }
     return mx;
@@ -1496,7 +1516,7 @@ inline int64_t flat_interleave_min() {
     static int64_t mn = -1;
     if (mn < 0) {
         const char *e = getenv("MHAQ_FQ_FLAT_INTERLEAVE_LOG2");
-        const int l2 = e ? atoi(e) : 62;
+        const int l2 = e ? atoi(e) : 24;
         mn = (int64_t)1 << (l2 < 0 ? 0 : (l2 > 62 ? 62 : l2));
     }
     return mn;
@@ -1516,8 +1536,17 @@ int launch_bwd_flat(bool explicit_r, const FlatGeom &f, cudaStream_t st, const f
                     const uint64_t *philox_dev, double *ws, unsigned int *ticket, float *o0, float *o1,
                     float *o2, float *o3) {
 #define MHAQ_FLAT(N)                                                                              \
-    fq_bwd_flat_kernel<METHOD, CLAMP, N><<<f.grid, kThreads, 0, st>>>(                            \
-        go, x, gx, prm, f, r, seed, offset, philox_dev, ws, ticket, o0, o1, o2, o3, flat_exp_flags())
+    do {                                                                                          \
+        static bool attr_set = false;                                                             \
+        if (!attr_set) {                                                                          \
+            cudaFuncSetAttribute(fq_bwd_flat_kernel<METHOD, CLAMP, N>,                            \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, kFlatSmemBytes);    \
+            attr_set = true;                                                                      \
+        }                                                                                         \
+        fq_bwd_flat_kernel<METHOD, CLAMP, N><<<f.grid, kFlatThreads, kFlatSmemBytes, st>>>(       \
+            go, x, gx, prm, f, r, seed, offset, philox_dev, ws, ticket, o0, o1, o2, o3,           \
+            flat_exp_flags());                                                                    \
+    } while (0)
     if (METHOD == MHAQ_FQ_LSQ) MHAQ_FLAT(NOISE_NONE);
     else if (explicit_r) MHAQ_FLAT(NOISE_EXPLICIT);
     else MHAQ_FLAT(NOISE_PHILOX);

@@ -15,8 +15,16 @@ The key is built from tensor identity + in-place version counters, so optimizer
 steps (`param.add_` bumps `_version`), `load_state_dict` (copy_) and calibration
 (which REPLACES the Parameter objects, minmaxobserver.py:59-66,86) all invalidate
 it.  Nothing is stored in the state dict.
+
+One thing the key cannot see: a write through ``param.data`` (``p.data.copy_()``, old-style EMA /
+weight clipping) does not bump ``param._version``.  With autograd on this does not matter (the
+entry is dropped by the backward pass of every step); code that mutates ``.data`` between two
+``no_grad`` forward calls must call ``layer._wq_cache.clear()`` (or use ``with torch.no_grad():
+p.copy_()``, which does bump the version).
 """
 from __future__ import annotations
+
+import weakref
 
 import torch
 
@@ -28,17 +36,23 @@ def _sig(t):
 
 
 class WeightQuantCache:
-    __slots__ = ("key", "value", "hits", "misses")
+    __slots__ = ("key", "value", "hits", "misses", "_refs", "_probe")
 
     def __init__(self):
         self.key = None
         self.value = None
         self.hits = 0
         self.misses = 0
+        self._refs = ()       # weak references to the tensors the entry was computed from
+        self._probe = ()
 
     def lookup(self, tensors, grad_mode: bool, training: bool):
         key = (tuple(_sig(t) for t in tensors), grad_mode, training)
-        if self.key == key and self.value is not None:
+        self._probe = tensors
+        if self.key == key and self.value is not None and len(self._refs) == len(tensors) and all(
+                (r is None and t is None) or (r is not None and r() is t) for r, t in zip(self._refs, tensors)):
+            # identity, not just id(): a re-bound Parameter (calibration replaces them) may reuse the
+            # id, data_ptr and version 0 of a tensor that has been freed
             self.hits += 1
             return key, self.value
         self.misses += 1
@@ -46,6 +60,7 @@ class WeightQuantCache:
 
     def store(self, key, value):
         self.key, self.value = key, value
+        self._refs = tuple(None if t is None else weakref.ref(t) for t in self._probe)
         cache = self
 
         def _drop(grad, _key=key):
@@ -59,4 +74,4 @@ class WeightQuantCache:
                 t.register_hook(_drop)
 
     def clear(self):
-        self.key, self.value = None, None
+        self.key, self.value, self._refs = None, None, ()
