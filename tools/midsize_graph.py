@@ -85,10 +85,12 @@ def case(name, shape, per_channel, method="STE", clamp=True):
     mid = ops._method_id(method)
     f = lambda i: ops._forward_impl(xs[i], Ls[i], True, False, False)
     b = lambda i: ops._backward_impl(gs[i], xs[i], Ls[i], mid, False, None, True, philox=(1, 2))
+    ev = lambda i: ops._forward_impl(xs[i], Ls[i], True, False, True)     # eval: y + code / input min-max
     cp = lambda i: outs[i].copy_(xs[i])
     ad = lambda i: torch.add(xs[i], gs[i], out=outs[i])
     r = {"name": name, "shape": list(shape), "n": n, "K": K, "method": method}
-    for key, fn, by in (("fwd", f, 8), ("bwd", b, 12 + (8 if method == "AEWGS" else 0)), ("copy", cp, 8), ("add3", ad, 12)):
+    for key, fn, by in (("fwd", f, 8), ("eval", ev, 8), ("bwd", b, 12 + (8 if method == "AEWGS" else 0)), ("copy", cp, 8),
+                        ("add3", ad, 12)):
         tg = graph_time(fn, K)
         te = eager_time(fn, K)
         r[key] = {"graph_us": round(tg * 1e3, 2), "eager_us": round(te * 1e3, 2),
@@ -96,6 +98,7 @@ def case(name, shape, per_channel, method="STE", clamp=True):
     r["fwd_vs_copy"] = round(r["copy"]["graph_us"] / r["fwd"]["graph_us"], 3)
     r["bwd_vs_add3"] = round(r["add3"]["graph_us"] / r["bwd"]["graph_us"], 3)
     print(f"{name:34s} n={n/1e6:7.2f}M  fwd {r['fwd']['graph_us']:7.1f} us ({r['fwd']['frac_peak']:.2f}; copy {r['copy']['graph_us']:6.1f} us; eager {r['fwd']['eager_us']:6.1f})"
+          f"  eval {r['eval']['graph_us']:7.1f} us ({r['eval']['frac_peak']:.2f})"
           f"  bwd {r['bwd']['graph_us']:7.1f} us ({r['bwd']['frac_peak']:.2f}; add3 {r['add3']['graph_us']:6.1f} us; eager {r['bwd']['eager_us']:6.1f})", flush=True)
     return r
 
