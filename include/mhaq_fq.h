@@ -253,9 +253,17 @@ typedef struct {
     int64_t n_rows, n_inner;
 } mhaq_fq_wrow_bwd_desc;
 int mhaq_fq_wrow_multi_fwd_f32(const mhaq_fq_wrow_fwd_desc *descs, int n_tensors, void *stream);
+/* AEWGS (the one estimator with an exchange step) in the multi-tensor form: first
+ * mhaq_fq_wrow_multi_aewgs_stats_f32 writes the per-row means of sign(g)*e, e*e, e of EVERY tensor
+ * into one packed buffer stats[3][total_rows] (rows of tensor 0, then tensor 1, ...); the caller
+ * all-reduces (AVG) that buffer ONCE for the whole model — the reference issues three all-reduces per
+ * weight tensor, gdnsq.py:126-129 — and passes it to mhaq_fq_wrow_multi_bwd_f32(method = AEWGS).
+ * For the other methods aewgs_stats is NULL and total_rows ignored. */
+int mhaq_fq_wrow_multi_aewgs_stats_f32(const mhaq_fq_wrow_bwd_desc *descs, int n_tensors,
+                                       float *stats, int64_t total_rows, void *stream);
 int mhaq_fq_wrow_multi_bwd_f32(const mhaq_fq_wrow_bwd_desc *descs, int n_tensors, int method,
                                uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
-                               void *stream);
+                               const float *aewgs_stats, int64_t total_rows, void *stream);
 
 /* PotentialLoss's bit-width constraint (gdnsq_loss.py:32-86 / 114-168, exponent p = 1 as
  * GDNSQQuant passes it, gdnsq_quant.py:90-102) in ONE launch:

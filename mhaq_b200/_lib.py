@@ -59,7 +59,8 @@ _SIGNATURES = {
     "mhaq_fq_rowstat_f32": (c_int, [_P, c_int64, c_int64, _P, _P, _P, _P, _P]),
     "mhaq_fq_rowstat_bwd_f32": (c_int, [_P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mhaq_fq_wrow_multi_fwd_f32": (c_int, [_P, c_int, _P]),
-    "mhaq_fq_wrow_multi_bwd_f32": (c_int, [_P, c_int, c_int, c_uint64, c_uint64, _P, _P]),
+    "mhaq_fq_wrow_multi_aewgs_stats_f32": (c_int, [_P, c_int, _P, c_int64, _P]),
+    "mhaq_fq_wrow_multi_bwd_f32": (c_int, [_P, c_int, c_int, c_uint64, c_uint64, _P, _P, c_int64, _P]),
     "mhaq_fq_potential_loss_fwd_f32": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, _P, c_float, c_float,
                                                c_float, c_float, c_int, c_int, _P, _P]),
     "mhaq_fq_potential_loss_bwd_f32": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_float, c_float,

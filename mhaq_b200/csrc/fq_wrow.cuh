@@ -150,6 +150,7 @@ struct WRowBwdRow {
     float *gw, *g_log_s;         // this row's outputs (either may be NULL)
     float log_s, mn, mx;         // log_wght_s[row], row minimum / maximum from the forward
     float g_lr, g_mn, g_mx;      // gradients w.r.t. log_range / row_min / row_max of this row
+    float delta;                 // AEWGS: this channel's delta from the (all-reduced) statistics
     bool has_glr, has_gmn, has_gmx;
     int64_t noise_row;           // row index inside ITS tensor: the noise stream's coordinate
 };
@@ -175,7 +176,7 @@ __device__ __forceinline__ void wrow_bwd_row(const WRowBwdRow &d, int64_t n_inne
     BwdConst bc;
     bc.smul = q.s;
     bc.rcp = __frcp_rn(q.s);
-    bc.delta = 0.f;
+    bc.delta = d.delta;
     bc.lo_lt_hi = true;
     bc.lo_gt_hi = false;
     Acc acc = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -307,6 +308,7 @@ fq_wrow_bwd_kernel(const float *__restrict__ go, const float *__restrict__ w, WR
         d.g_mn = d.has_gmn ? __ldg(g_row_min + row) : 0.f;
         d.g_mx = d.has_gmx ? __ldg(g_row_max + row) : 0.f;
         d.noise_row = row;
+        d.delta = 0.f;
         wrow_bwd_row<METHOD, NOISE, VEC>(d, a.n_inner, key, s_red, s_d);
     }
 }
@@ -327,10 +329,14 @@ struct WRowBwdMulti {
 
 // Tensor t draws its noise from Philox stream (seed, offset + t): the stream a per-layer launch
 // with that offset would read.
+// AEWGS: `stats` = packed per-row means [3][total rows of the launch's model] (num | e2 | me), already
+// averaged over the ranks; `stats_row0` = index of this launch's first row in it, `stats_ld` = its
+// leading dimension (gdnsq.py:126-134).
 template <int METHOD, int NOISE>
 __global__ void __launch_bounds__(kThreads)
 fq_wrow_multi_bwd_kernel(const __grid_constant__ WRowBwdMulti m, uint64_t seed, uint64_t offset,
-                         const uint64_t *__restrict__ philox_dev) {
+                         const uint64_t *__restrict__ philox_dev, const float *__restrict__ stats,
+                         int64_t stats_row0, int64_t stats_ld) {
     __shared__ float s_red[5][kThreads / 32];
     __shared__ float s_d[2];
     const int total = m.row0[m.n];
@@ -353,7 +359,88 @@ fq_wrow_multi_bwd_kernel(const __grid_constant__ WRowBwdMulti m, uint64_t seed, 
         d.g_mn = d.has_gmn ? __ldg(e.g_row_min + r) : 0.f;
         d.g_mx = d.has_gmx ? __ldg(e.g_row_max + r) : 0.f;
         d.noise_row = r;
+        d.delta = 0.f;
+        if (METHOD == MHAQ_FQ_AEWGS) {
+            const int64_t sr = stats_row0 + row;
+            const float num = __ldg(stats + sr), e2 = __ldg(stats + stats_ld + sr), me = __ldg(stats + 2 * stats_ld + sr);
+            float den = f_sub(e2, f_mul(me, me));                 // gdnsq.py:132
+            den = (den < kAewgsEps) ? kAewgsEps : den;            // clamp_min(eps)
+            d.delta = f_div(num, den);                            // gdnsq.py:134
+        }
         if (m.vec[t]) wrow_bwd_row<METHOD, NOISE, true>(d, e.n_inner, key, s_red, s_d);
         else wrow_bwd_row<METHOD, NOISE, false>(d, e.n_inner, key, s_red, s_d);
+    }
+}
+
+// ---- AEWGS statistics of every row of every tensor, one grid (gdnsq.py:118-124) --------------
+// stats[0][row] = mean(sign(g) * e), stats[1][row] = mean(e * e), stats[2][row] = mean(e) over the
+// row, g = go * s, e = round(v) - v: the packed buffer the caller all-reduces ONCE for the whole
+// model (the reference: three all-reduces per weight tensor, gdnsq.py:126-129).
+template <bool VEC>
+__device__ __forceinline__ void wrow_aewgs_stats_row(const float *__restrict__ w_row,
+                                                     const float *__restrict__ go_row, float log_s, float mn,
+                                                     int64_t n_inner, float *o_num, float *o_e2, float *o_me,
+                                                     float (*s_red)[kThreads / 32]) {
+    const int tid = threadIdx.x;
+    const float s = exp2f(log_s);
+    float a_num = 0.f, a_e2 = 0.f, a_e = 0.f;
+    for (int64_t p = (int64_t)tid * 4; p < n_inner; p += kIterElems) {
+        const int nv = valid4<VEC>(p, n_inner);
+        const float4 xv = load4<VEC>(w_row, p, n_inner);
+        const float4 gv = load4<VEC>(go_row, p, n_inner);
+        const float xe[4] = {xv.x, xv.y, xv.z, xv.w}, ge[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i < nv) {
+                const float v = f_div(f_sub(xe[i], mn), s);
+                const float e = f_sub(rintf(v), v);
+                const float gg = f_mul(ge[i], s);
+                const float sg = (gg > 0.f) ? 1.f : ((gg < 0.f) ? -1.f : 0.f);
+                a_num += f_mul(sg, e);
+                a_e2 += f_mul(e, e);
+                a_e += e;
+            }
+        }
+    }
+    const float v0 = warp_sum(a_num), v1 = warp_sum(a_e2), v2 = warp_sum(a_e);
+    if ((tid & 31) == 0) {
+        const int wi = tid >> 5;
+        s_red[0][wi] = v0; s_red[1][wi] = v1; s_red[2][wi] = v2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double t[3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            t[m] = 0.0;
+#pragma unroll
+            for (int wi = 0; wi < kThreads / 32; ++wi) t[m] += (double)s_red[m][wi];
+        }
+        const double cnt = (double)n_inner;
+        *o_num = (float)(t[0] / cnt);
+        *o_e2 = (float)(t[1] / cnt);
+        *o_me = (float)(t[2] / cnt);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kThreads)
+fq_wrow_multi_aewgs_stats_kernel(const __grid_constant__ WRowBwdMulti m, float *__restrict__ stats,
+                                 int64_t stats_row0, int64_t stats_ld) {
+    __shared__ float s_red[5][kThreads / 32];
+    const int total = m.row0[m.n];
+    for (int row = blockIdx.x; row < total; row += gridDim.x) {
+        const int t = wrow_find(m.row0, m.n, row);
+        const WRowBwdDesc &e = m.d[t];
+        const int64_t r = row - m.row0[t];
+        const int64_t off = r * e.n_inner;
+        const int64_t sr = stats_row0 + row;
+        float *o0 = stats + sr, *o1 = stats + stats_ld + sr, *o2 = stats + 2 * stats_ld + sr;
+        if (m.vec[t])
+            wrow_aewgs_stats_row<true>(e.w + off, e.g_wq + off, __ldg(e.log_s + r), __ldg(e.row_min + r), e.n_inner,
+                                       o0, o1, o2, s_red);
+        else
+            wrow_aewgs_stats_row<false>(e.w + off, e.g_wq + off, __ldg(e.log_s + r), __ldg(e.row_min + r), e.n_inner,
+                                        o0, o1, o2, s_red);
     }
 }

@@ -1554,6 +1554,44 @@ int launch_bwd_flat(bool explicit_r, const FlatGeom &f, cudaStream_t st, const f
     return last_error();
 }
 
+// shared by the multi-tensor backward and the multi-tensor AEWGS statistics: validate, chunk, pack
+template <typename Launch>
+int wrow_multi_bwd_chunks(const mhaq_fq_wrow_bwd_desc *descs, int n_tensors, Launch launch) {
+    int64_t row_base = 0;
+    for (int c0 = 0; c0 < n_tensors; c0 += kWRowMultiBwdMax) {
+        WRowBwdMulti m;
+        m.n = 0;
+        m.row0[0] = 0;
+        // (every tensor of the chunk keeps a slot, empty ones included: slot index == noise stream index)
+        for (int i = c0; i < n_tensors && m.n < kWRowMultiBwdMax; ++i) {
+            const mhaq_fq_wrow_bwd_desc &d = descs[i];
+            const int k = m.n++;
+            m.d[k] = {d.g_wq, d.w, d.log_scale, d.row_min, d.row_max, d.g_log_range, d.g_row_min,
+                      d.g_row_max, d.r, d.g_w, d.g_log_scale, d.n_inner};
+            m.vec[k] = (d.n_inner % 4 == 0) && aligned16(d.w) && aligned16(d.g_wq) &&
+                       (!d.g_w || aligned16(d.g_w)) && (!d.r || aligned16(d.r));
+            m.row0[k + 1] = m.row0[k] + (int)d.n_rows;
+        }
+        if (m.row0[m.n] > 0) {
+            const int rc = launch(m, c0, row_base);
+            if (rc) return rc;
+        }
+        row_base += m.row0[m.n];
+    }
+    return 0;
+}
+
+int wrow_multi_check(const mhaq_fq_wrow_bwd_desc *descs, int n_tensors, bool *explicit_r) {
+    for (int i = 0; i < n_tensors; ++i) {
+        const mhaq_fq_wrow_bwd_desc &d = descs[i];
+        if (!d.g_wq || !d.w || !d.log_scale || !d.row_min || !d.row_max) return MHAQ_FQ_ENULL;
+        if (d.n_rows < 0 || d.n_inner <= 0 || d.n_rows > 0x3fffffff) return MHAQ_FQ_EINVAL;
+        if (i == 0) *explicit_r = d.r != nullptr;
+        else if ((d.r != nullptr) != *explicit_r) return MHAQ_FQ_EINVAL;   // all explicit or all in-kernel
+    }
+    return 0;
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -1871,50 +1909,52 @@ int mhaq_fq_wrow_multi_fwd_f32(const mhaq_fq_wrow_fwd_desc *descs, int n_tensors
     return 0;
 }
 
+int mhaq_fq_wrow_multi_aewgs_stats_f32(const mhaq_fq_wrow_bwd_desc *descs, int n_tensors, float *stats,
+                                       int64_t total_rows, void *stream) {
+    if (n_tensors < 0 || total_rows < 0) return MHAQ_FQ_EINVAL;
+    if (n_tensors == 0) return 0;
+    if (!descs || !stats) return MHAQ_FQ_ENULL;
+    bool er = false;
+    int rc = wrow_multi_check(descs, n_tensors, &er);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return wrow_multi_bwd_chunks(descs, n_tensors, [&](const WRowBwdMulti &m, int, int64_t row_base) {
+        if (row_base + m.row0[m.n] > total_rows) return (int)MHAQ_FQ_EINVAL;
+        fq_wrow_multi_aewgs_stats_kernel<<<grid_for(m.row0[m.n]), kThreads, 0, st>>>(m, stats, row_base, total_rows);
+        return last_error();
+    });
+}
+
 int mhaq_fq_wrow_multi_bwd_f32(const mhaq_fq_wrow_bwd_desc *descs, int n_tensors, int method,
-                               uint64_t seed, uint64_t offset, const uint64_t *philox_dev, void *stream) {
+                               uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                               const float *aewgs_stats, int64_t total_rows, void *stream) {
     if (n_tensors < 0) return MHAQ_FQ_EINVAL;
     if (n_tensors == 0) return 0;
     if (!descs) return MHAQ_FQ_ENULL;
-    if (method != MHAQ_FQ_STE && method != MHAQ_FQ_EWGS && method != MHAQ_FQ_LSQ) return MHAQ_FQ_EINVAL;
+    if (method < 0 || method > 3) return MHAQ_FQ_EINVAL;
+    if (method == MHAQ_FQ_AEWGS && !aewgs_stats) return MHAQ_FQ_ENULL;
     bool explicit_r = false;
-    for (int i = 0; i < n_tensors; ++i) {
-        const mhaq_fq_wrow_bwd_desc &d = descs[i];
-        if (!d.g_wq || !d.w || !d.log_scale || !d.row_min || !d.row_max) return MHAQ_FQ_ENULL;
-        if (d.n_rows < 0 || d.n_inner <= 0 || d.n_rows > 0x3fffffff) return MHAQ_FQ_EINVAL;
-        if (i == 0) explicit_r = d.r != nullptr;
-        else if ((d.r != nullptr) != explicit_r) return MHAQ_FQ_EINVAL;   // all explicit or all in-kernel
-    }
+    int rc = wrow_multi_check(descs, n_tensors, &explicit_r);
+    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    for (int c0 = 0; c0 < n_tensors; c0 += kWRowMultiBwdMax) {
-        WRowBwdMulti m;
-        m.n = 0;
-        m.row0[0] = 0;
-        // (every tensor of the chunk keeps a slot, empty ones included: slot index == noise stream index)
-        for (int i = c0; i < n_tensors && m.n < kWRowMultiBwdMax; ++i) {
-            const mhaq_fq_wrow_bwd_desc &d = descs[i];
-            const int k = m.n++;
-            m.d[k] = {d.g_wq, d.w, d.log_scale, d.row_min, d.row_max, d.g_log_range, d.g_row_min,
-                      d.g_row_max, d.r, d.g_w, d.g_log_scale, d.n_inner};
-            m.vec[k] = (d.n_inner % 4 == 0) && aligned16(d.w) && aligned16(d.g_wq) &&
-                       (!d.g_w || aligned16(d.g_w)) && (!d.r || aligned16(d.r));
-            m.row0[k + 1] = m.row0[k] + (int)d.n_rows;
-        }
-        if (m.row0[m.n] == 0) continue;
+    return wrow_multi_bwd_chunks(descs, n_tensors, [&](const WRowBwdMulti &m, int c0, int64_t row_base) {
         const int grid = grid_for(m.row0[m.n]);
         const uint64_t off = offset + (uint64_t)c0;
-#define MHAQ_WMULTI(M, N) fq_wrow_multi_bwd_kernel<M, N><<<grid, kThreads, 0, st>>>(m, seed, off, philox_dev)
+        if (method == MHAQ_FQ_AEWGS && row_base + m.row0[m.n] > total_rows) return (int)MHAQ_FQ_EINVAL;
+#define MHAQ_WMULTI(M, N)                                                                        \
+    fq_wrow_multi_bwd_kernel<M, N><<<grid, kThreads, 0, st>>>(m, seed, off, philox_dev, aewgs_stats, \
+                                                             row_base, total_rows)
         if (method == MHAQ_FQ_LSQ) MHAQ_WMULTI(MHAQ_FQ_LSQ, NOISE_NONE);
         else if (method == MHAQ_FQ_STE) {
             if (explicit_r) MHAQ_WMULTI(MHAQ_FQ_STE, NOISE_EXPLICIT); else MHAQ_WMULTI(MHAQ_FQ_STE, NOISE_PHILOX);
-        } else {
+        } else if (method == MHAQ_FQ_EWGS) {
             if (explicit_r) MHAQ_WMULTI(MHAQ_FQ_EWGS, NOISE_EXPLICIT); else MHAQ_WMULTI(MHAQ_FQ_EWGS, NOISE_PHILOX);
+        } else {
+            if (explicit_r) MHAQ_WMULTI(MHAQ_FQ_AEWGS, NOISE_EXPLICIT); else MHAQ_WMULTI(MHAQ_FQ_AEWGS, NOISE_PHILOX);
         }
 #undef MHAQ_WMULTI
-        const int rc = last_error();
-        if (rc) return rc;
-    }
-    return 0;
+        return last_error();
+    });
 }
 
 int mhaq_fq_potential_loss_fwd_f32(const float *log_act_s, const float *log_act_q, int64_t n_act,

@@ -789,10 +789,13 @@ def weight_fake_quant_log(w, log_wght_s, method="STE", noise=None, philox=None):
 WROW_MAX_INNER = 16384       # one CTA per row: conv / linear weight rows, not long tensors
 
 
-def weight_rows_fusable(w, log_wght_s, method) -> bool:
+def weight_rows_fusable(w, log_wght_s, method, multi: bool = False) -> bool:
+    """Row-resident kernels: one log-scale per row of dim 0, short rows.  A single-tensor launch
+    cannot serve AEWGS (its statistics are all-reduced between two passes); the multi-tensor
+    form can — statistics kernel, ONE all-reduce for the whole model, apply kernel."""
     rows = w.shape[0] if w.dim() >= 1 else 0
     return (rows > 0 and log_wght_s.numel() == rows and 0 < w.numel() // rows <= WROW_MAX_INNER
-            and _method_id(method) != METHOD_IDS["AEWGS"])
+            and (multi or _method_id(method) != METHOD_IDS["AEWGS"]))
 
 
 class _WeightRowFn(torch.autograd.Function):
@@ -936,7 +939,18 @@ class _WeightRowMultiFn(torch.autograd.Function):
             glss.append(None if gls is None else gls.reshape(ls.shape))
             r0 = r1
         seed, offset, pdev = (0, 0, None) if ctx.noises is not None else _philox_streams(ws[0], ctx.method, n, ctx.philox)
-        check(lib.mhaq_fq_wrow_multi_bwd_f32(descs, n, ctx.method, seed, offset, _ptr(pdev), _stream()),
+        ae_stats, total_rows = None, 0
+        if ctx.method == METHOD_IDS["AEWGS"]:
+            # the path's one exchange step, ONCE for the whole model: per-row statistics of every
+            # tensor -> one packed [3, total_rows] AVG all-reduce -> apply (gdnsq.py:118-134; the
+            # reference issues three all-reduces per weight tensor)
+            total_rows = sum(rows)
+            ae_stats = torch.empty(3 * total_rows, dtype=torch.float32, device=ws[0].device)
+            check(lib.mhaq_fq_wrow_multi_aewgs_stats_f32(descs, n, _ptr(ae_stats), total_rows, _stream()),
+                  "mhaq_fq_wrow_multi_aewgs_stats_f32")
+            ae_stats = allreduce_packed_stats(ae_stats)
+        check(lib.mhaq_fq_wrow_multi_bwd_f32(descs, n, ctx.method, seed, offset, _ptr(pdev), _ptr(ae_stats),
+                                             total_rows, _stream()),
               "mhaq_fq_wrow_multi_bwd_f32")
         return (None, None, None, None, *gws, *glss)
 
@@ -950,9 +964,9 @@ def weight_fake_quant_rows_multi(weights, log_scales, method="STE", noises=None,
     mid = _method_id(method)
     for w, ls in zip(weights, log_scales):
         _require_cuda(w)
-        if not weight_rows_fusable(w, ls, mid):
-            raise RuntimeError("weight_fake_quant_rows_multi: every tensor needs one log-scale per row of dim 0, "
-                               f"rows of at most {WROW_MAX_INNER} elements and a method other than AEWGS")
+        if not weight_rows_fusable(w, ls, mid, multi=True):
+            raise RuntimeError("weight_fake_quant_rows_multi: every tensor needs one log-scale per row of dim 0 "
+                               f"and rows of at most {WROW_MAX_INNER} elements")
     if mid == METHOD_IDS["LSQ"]:
         noises = None
     out = _WeightRowMultiFn.apply(mid, noises, philox, n, *weights, *log_scales)

@@ -7,7 +7,9 @@ model_helper.py:24-25,44).
 weights of all eligible `NoisyConv2d` layers with `ops.weight_fake_quant_rows_multi` and installs
 the results as the layers' per-step cache entries, so each layer's `forward` (and
 `ModelHelper.get_model_values`) finds its quantized weight, row range and log-range term ready.
-Layers it cannot take (per-tensor, AEWGS, quantized bias, long rows, CPU) keep their own path; a
+AEWGS — the one estimator with an exchange step — is served too: one statistics launch, ONE packed
+all-reduce for the whole model (the reference: three per weight tensor, gdnsq.py:126-129), one apply
+launch.  Layers it cannot take (per-tensor, quantized bias, long rows, CPU) keep their own path; a
 model driven without this call (e.g. the reference's own GDNSQQuant on these layer classes) simply
 quantizes layer by layer.
 """

@@ -98,7 +98,7 @@ class NoisyConv2d(nn.Conv2d):
         """May this layer's weight be quantized by the model-wide multi-tensor launch?"""
         from .... import ops
         return (is_per_channel(self.qscheme) and not self.quant_bias and self.positive_scale_ok()
-                and ops.weight_rows_fusable(self.weight, self.log_wght_s, self.Q._method()))
+                and ops.weight_rows_fusable(self.weight, self.log_wght_s, self.Q._method(), multi=True))
 
     def cache_probe(self):
         """(key, hit) of this step's weight-cache entry."""
