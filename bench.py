@@ -369,8 +369,11 @@ def qat_leg(a, dev, world, rank, use_dist, spec, ref_flags=False, profile_share=
             ops.allreduce_packed_stats = orig
         tot = sum(e0.elapsed_time(e1) for e0, e1 in evs)
         res["aewgs_stats_allreduce"] = {"calls_per_step": len(evs) // 3, "ms_per_step": round(tot / 3, 3),
-                                        "what": "packed [3,O] AVG all-reduce between the statistics and the apply "
-                                                "kernel, one per AEWGS weight tensor (eager DDP steps, CUDA events)"}
+                                        "what": "the path's one collective: packed [3, rows] AVG all-reduce between the "
+                                                "statistics and the apply kernel — ONE per step for all conv weights of the "
+                                                "model (the reference: 3 per weight tensor).  Stream time between CUDA events "
+                                                "recorded right before and after the call in eager DDP steps: NCCL launch + "
+                                                "transfer + waiting for the slowest rank to reach this point of its backward"}
 
     graphed = None
     if graph:

@@ -112,10 +112,10 @@ int64_t mhaq_fq_ticket_count(int64_t n_rows, int64_t n_inner, int64_t n_ch);
  * fp32 rounding (no FMA contraction, true division, round-half-even).
  *   y      : fake-quantized output, or NULL
  *   codes  : integer-valued fp32 codes rint(v), or NULL
- *   minmax_ws : NULL, or a workspace (mhaq_fq_workspace_bytes) that receives per-CTA
- *            {min code, max code, min input, max input} records for mhaq_fq_minmax_finalize
- *            (eval mode / calibration; NaN-propagating like torch.aminmax).  The statistics ride
- *            the same packed fast path as the plain forward (persistent grid, one record per CTA). */
+ *   minmax_ws : NULL, or a workspace (mhaq_fq_workspace_bytes) that receives one 16-byte
+ *            {min code, max code, min input, max input} record per task for
+ *            mhaq_fq_minmax_finalize (eval mode / calibration; NaN-propagating like
+ *            torch.aminmax).  The statistics ride the same packed fast path as the plain forward. */
 int mhaq_fq_fwd_f32(const float *x, float *y, float *codes,
                     const float *scale, const float *zp, const float *lo, const float *hi,
                     int scale_stride, int zp_stride, int lo_stride, int hi_stride, int param_mode,

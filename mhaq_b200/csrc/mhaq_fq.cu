@@ -102,19 +102,19 @@ __device__ __forceinline__ float absmax4(float m, const float4 &v) {
     return fmaxf(fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
 }
 
-// STATS = false: one CTA per task (grid = n_tasks), no statistics — the training forward.
-// STATS = true : persistent (grid <= kEvalGridCap), every CTA walks tasks blockIdx.x, +gridDim.x, ...
-//                keeps its running min / max in registers (min / max are exact and order-free, so
-//                the assignment of tasks to CTAs does not matter) and writes ONE record at the end.
-constexpr int kEvalGridCap = 148 * 8;
-
+// One CTA per task (grid = n_tasks) in both modes; the hardware block scheduler balances the SMs.
+// STATS = true additionally keeps running min / max of codes and inputs per task and writes one
+// 16-byte record {cmin, cmax, xmin, xmax} per task (min / max are exact and order-free).  A
+// persistent variant (one record per CTA, 148 x 8 CTAs) was measured at 0.82-0.86 of the copy
+// peak against 1.03 for the plain forward (profiles/r02_exp_eval_persistent.txt) and dropped.
 template <bool VEC, bool CLAMP, bool STATS>
 __global__ void __launch_bounds__(kThreads)
 fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restrict__ codes,
               QParams prm, Geom g, double *__restrict__ mm_ws) {
     const int tid = threadIdx.x;
-    FwdStat st = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+    __shared__ float s_red[4][kThreads / 32];
     for (int64_t t = blockIdx.x; t < g.n_tasks; t += gridDim.x) {
+        FwdStat st = {INFINITY, -INFINITY, INFINITY, -INFINITY};
         const Task k = make_task(g, t);
         const QConst q = load_qconst(prm, k.ch);
         const Div2 dv = make_div2(q.s, __frcp_rn(q.s));
@@ -195,58 +195,59 @@ fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restr
                 }
             }
         }
-    }
-    if (STATS) {
-        __shared__ float s_red[4][kThreads / 32];
-        const float a = warp_min_nan(st.cmin), b = warp_max_nan(st.cmax);
-        const float c = warp_min_nan(st.xmin), d = warp_max_nan(st.xmax);
-        if ((tid & 31) == 0) {
-            s_red[0][tid >> 5] = a; s_red[1][tid >> 5] = b;
-            s_red[2][tid >> 5] = c; s_red[3][tid >> 5] = d;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            float r0 = s_red[0][0], r1 = s_red[1][0], r2 = s_red[2][0], r3 = s_red[3][0];
-            for (int w = 1; w < kThreads / 32; ++w) {
-                r0 = min_nan(r0, s_red[0][w]); r1 = max_nan(r1, s_red[1][w]);
-                r2 = min_nan(r2, s_red[2][w]); r3 = max_nan(r3, s_red[3][w]);
+            if (STATS) {
+            const float a = warp_min_nan(st.cmin), b = warp_max_nan(st.cmax);
+            const float c = warp_min_nan(st.xmin), d = warp_max_nan(st.xmax);
+            if ((tid & 31) == 0) {
+                s_red[0][tid >> 5] = a; s_red[1][tid >> 5] = b;
+                s_red[2][tid >> 5] = c; s_red[3][tid >> 5] = d;
             }
-            float *rec = reinterpret_cast<float *>(mm_ws + (int64_t)blockIdx.x * kNPart);
-            rec[0] = r0; rec[1] = r1; rec[2] = r2; rec[3] = r3;
+            __syncthreads();
+            if (tid == 0) {
+                float r0 = s_red[0][0], r1 = s_red[1][0], r2 = s_red[2][0], r3 = s_red[3][0];
+                for (int w = 1; w < kThreads / 32; ++w) {
+                    r0 = min_nan(r0, s_red[0][w]); r1 = max_nan(r1, s_red[1][w]);
+                    r2 = min_nan(r2, s_red[2][w]); r3 = max_nan(r3, s_red[3][w]);
+                }
+                reinterpret_cast<float4 *>(mm_ws)[t] = make_float4(r0, r1, r2, r3);
+            }
+            __syncthreads();
         }
     }
 }
 
-// out5 = {min code, max code, non-finite flag, min input, max input} from the per-CTA records
-__global__ void __launch_bounds__(256)
+// out5 = {min code, max code, non-finite flag, min input, max input} from the per-task records
+// (one 128-bit load per record, every load of a thread independent of the others)
+constexpr int kMmThreads = 1024;
+__global__ void __launch_bounds__(kMmThreads)
 fq_minmax_finalize_kernel(const double *__restrict__ ws, int64_t n_rec, float *__restrict__ out5) {
-    __shared__ float s[4][256];
+    __shared__ float s[4][kMmThreads / 32];
+    const float4 *rec = reinterpret_cast<const float4 *>(ws);
     float v[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
-    for (int64_t t = threadIdx.x; t < n_rec; t += 256) {
-        const float *rec = reinterpret_cast<const float *>(ws + t * kNPart);
-        v[0] = min_nan(v[0], rec[0]); v[1] = max_nan(v[1], rec[1]);
-        v[2] = min_nan(v[2], rec[2]); v[3] = max_nan(v[3], rec[3]);
+    for (int64_t t = threadIdx.x; t < n_rec; t += kMmThreads) {
+        const float4 r = __ldg(rec + t);
+        v[0] = min_nan(v[0], r.x); v[1] = max_nan(v[1], r.y);
+        v[2] = min_nan(v[2], r.z); v[3] = max_nan(v[3], r.w);
     }
+    v[0] = warp_min_nan(v[0]); v[1] = warp_max_nan(v[1]);
+    v[2] = warp_min_nan(v[2]); v[3] = warp_max_nan(v[3]);
+    if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int m = 0; m < 4; ++m) s[m][threadIdx.x] = v[m];
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if ((int)threadIdx.x < o) {
-            s[0][threadIdx.x] = min_nan(s[0][threadIdx.x], s[0][threadIdx.x + o]);
-            s[1][threadIdx.x] = max_nan(s[1][threadIdx.x], s[1][threadIdx.x + o]);
-            s[2][threadIdx.x] = min_nan(s[2][threadIdx.x], s[2][threadIdx.x + o]);
-            s[3][threadIdx.x] = max_nan(s[3][threadIdx.x], s[3][threadIdx.x + o]);
-        }
-        __syncthreads();
+        for (int m = 0; m < 4; ++m) s[m][threadIdx.x >> 5] = v[m];
     }
-    if (threadIdx.x == 0) {
-        const float cmin = s[0][0], cmax = s[1][0];
-        out5[0] = cmin;
-        out5[1] = cmax;
-        // every code is finite  <=>  both extremes are (NaN propagates into both)
-        out5[2] = (fabsf(cmin) < INFINITY && fabsf(cmax) < INFINITY) ? 0.f : 1.f;
-        out5[3] = s[2][0];
-        out5[4] = s[3][0];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int l = threadIdx.x;
+        const float a = warp_min_nan(s[0][l]), b = warp_max_nan(s[1][l]);
+        const float c = warp_min_nan(s[2][l]), d = warp_max_nan(s[3][l]);
+        if (l == 0) {
+            out5[0] = a;
+            out5[1] = b;
+            // every code is finite  <=>  both extremes are (NaN propagates into both)
+            out5[2] = (fabsf(a) < INFINITY && fabsf(b) < INFINITY) ? 0.f : 1.f;
+            out5[3] = c;
+            out5[4] = d;
+        }
     }
 }
 
@@ -1430,10 +1431,6 @@ inline Geom reduce_geom(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
     return make_geom(n_rows, n_inner, n_ch, GEOM_REDUCE, ov);
 }
 
-inline int eval_grid(int64_t n_tasks) {
-    return (int)(n_tasks < kEvalGridCap ? n_tasks : kEvalGridCap);
-}
-
 inline int last_error() {
     cudaError_t e = cudaGetLastError();
     return (int)e;
@@ -1648,14 +1645,13 @@ int mhaq_fq_fwd_f32(const float *x, float *y, float *codes, const float *scale, 
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = grid_for(g.n_tasks);
     const bool clamp = has_clamp(param_mode, lo, hi);
-    if (minmax_ws) {      // eval statistics: persistent, one record per CTA
-        const int eg = eval_grid(g.n_tasks);
+    if (minmax_ws) {      // eval statistics: one 16-byte record per task
         if (vec && clamp)
-            fq_fwd_kernel<true, true, true><<<eg, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+            fq_fwd_kernel<true, true, true><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
         else if (vec)
-            fq_fwd_kernel<true, false, true><<<eg, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+            fq_fwd_kernel<true, false, true><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
         else
-            fq_fwd_kernel<false, true, true><<<eg, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
+            fq_fwd_kernel<false, true, true><<<grid, kThreads, 0, st>>>(x, y, codes, prm, g, minmax_ws);
         return last_error();
     }
     if (vec && clamp)
@@ -1672,7 +1668,7 @@ int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_i
     if (!minmax_ws || !out5) return MHAQ_FQ_ENULL;
     const int64_t n_tasks = mhaq_fq_num_tasks(n_rows, n_inner);
     if (n_tasks <= 0) return MHAQ_FQ_EINVAL;
-    fq_minmax_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(minmax_ws, eval_grid(n_tasks), out5);
+    fq_minmax_finalize_kernel<<<1, kMmThreads, 0, (cudaStream_t)stream>>>(minmax_ws, n_tasks, out5);
     return last_error();
 }
 

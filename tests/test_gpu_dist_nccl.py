@@ -135,6 +135,31 @@ def _worker(rank, world, port, q):
             "g_weight_err_over_tol": float(((gw_o - gw_r).abs() / (gw_r.abs() * 1e-5 + 1e-5 * float(gw_r.abs().max()))).max()),
             "g_log_wght_s_err_over_tol": float(((gs_o - gs_r).abs() / (gs_r.abs() * 1e-5 + 2e-5)).max()),
         }
+        # --- model-wide form: statistics of EVERY tensor -> ONE all-reduce -> apply, against the
+        # per-layer streaming path (pinned against the reference above) on the same two ranks
+        gm = torch.Generator().manual_seed(11)
+        shapes = [(16, 8, 3, 3), (24, 16, 3, 3), (10, 50)]
+        Ws = [(torch.randn(s_, generator=gm) * 0.2).to(dev) for s_ in shapes]
+        Ls = [torch.full((s_[0],) + (1,) * (len(s_) - 1), -3.5).to(dev) for s_ in shapes]
+        gr2 = torch.Generator().manual_seed(70 + rank)
+        Gs = [torch.randn(s_, generator=gr2).to(dev) for s_ in shapes]
+        Ns = [(torch.randint(0, 2, s_, generator=gr2).float() - 0.5).to(dev) for s_ in shapes]
+        per_layer = []
+        for w_, l_, g_, n_ in zip(Ws, Ls, Gs, Ns):
+            wl, ll = w_.clone().requires_grad_(True), l_.clone().requires_grad_(True)
+            wq_, _, _ = ops.weight_fake_quant_log(wl, ll, method="AEWGS", noise=n_)
+            wq_.backward(g_)
+            per_layer.append((wl.grad, ll.grad))
+        Wm = [w_.clone().requires_grad_(True) for w_ in Ws]
+        Lm = [l_.clone().requires_grad_(True) for l_ in Ls]
+        outs = ops.weight_fake_quant_rows_multi(Wm, Lm, method="AEWGS", noises=Ns)
+        sum((o[0] * g_).sum() for o, g_ in zip(outs, Gs)).backward()
+        torch.cuda.synchronize()
+        worst = 0.0
+        for (gw_r2, gl_r2), wm, lm in zip(per_layer, Wm, Lm):
+            worst = max(worst, float(((wm.grad - gw_r2).abs() / (gw_r2.abs() * 1e-5 + 2e-5)).max()),
+                        float(((lm.grad - gl_r2).abs() / (gl_r2.abs() * 1e-5 + 2e-5)).max()))
+        res["multi_tensor_vs_per_layer_err_over_tol"] = worst
         q.put(res)
     except Exception as exc:       # surface the failure in the parent instead of a silent hang
         import traceback
@@ -174,5 +199,6 @@ def test_two_rank_nccl_aewgs_cuda_path_matches_the_live_reference():
             assert c["g_zp_err_over_tol"] <= 1.0, (d["rank"], tag, c)
         assert d["layer"]["g_weight_err_over_tol"] <= 1.0, d
         assert d["layer"]["g_log_wght_s_err_over_tol"] <= 1.0, d
+        assert d["multi_tensor_vs_per_layer_err_over_tol"] <= 1.0, d
     # different shards -> different per-rank gradients (the exchange really mixed two ranks' data)
     assert out[0]["per_channel"]["gx_checksum"] != out[1]["per_channel"]["gx_checksum"]

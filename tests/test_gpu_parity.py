@@ -835,3 +835,43 @@ def test_fused_potential_loss_matches_the_torch_expression(fq, n_w, n_a, lossles
         for a, b in zip(logs_f, logs_t):
             H.assert_close_rel(a, b, 1e-6, "logged term", abs_floor=1e-7)
         assert abs(ls_f - ls_t) <= 1e-6 * abs(ls_t) and c_f == c_t
+
+
+@pytest.mark.parametrize("n_tensors", [5, 30])
+def test_multi_tensor_aewgs_equals_the_streaming_aewgs_path(fq, n_tensors):
+    """AEWGS weights, model-wide: statistics kernel -> ONE packed all-reduce (a no-op on one rank)
+    -> apply kernel, against the per-layer streaming path (row statistics, forward, AEWGS statistics
+    + finalize, backward + finalize, amin scatter) that the goldens and the live-reference tests pin."""
+    ops = fq.ops
+    g = torch.Generator().manual_seed(100 + n_tensors)
+    shapes = [MULTI_SHAPES[i % len(MULTI_SHAPES)] for i in range(n_tensors)]
+    ws = [(torch.randn(s, generator=g) * 0.2).cuda() for s in shapes]
+    lss = [(torch.full((s[0],) + (1,) * (len(s) - 1), -3.0) + 0.5 * torch.rand((s[0],) + (1,) * (len(s) - 1), generator=g)).cuda()
+           for s in shapes]
+    gos = [torch.randn(s, generator=g).cuda() for s in shapes]
+    gls = [torch.randn(s[0], generator=g).cuda() for s in shapes]
+    noises = [(torch.randint(0, 2, s, generator=g).float() - 0.5).cuda() for s in shapes]
+    ref = []
+    for i in range(n_tensors):
+        w, ls = ws[i].clone().requires_grad_(True), lss[i].clone().requires_grad_(True)
+        wq, mn, mx = ops.weight_fake_quant_log(w, ls, method="AEWGS", noise=noises[i])
+        lr = torch.log2(mx - mn + torch.exp2(ls.ravel()))
+        ((wq * gos[i]).sum() + (lr * gls[i]).sum()).backward()
+        ref.append((wq.detach(), lr.detach(), w.grad, ls.grad))
+    W = [w.clone().requires_grad_(True) for w in ws]
+    L = [l.clone().requires_grad_(True) for l in lss]
+    res = ops.weight_fake_quant_rows_multi(W, L, method="AEWGS", noises=noises)
+    loss = sum((wq * go).sum() + (lr * gl).sum() for (wq, mn, mx, lr), go, gl in zip(res, gos, gls))
+    loss.backward()
+    for i, ((wq, mn, mx, lr), (wq_r, lr_r, gw_r, gls_r)) in enumerate(zip(res, ref)):
+        assert torch.equal(wq.detach(), wq_r), (i, shapes[i])
+        assert torch.equal(lr.detach(), lr_r), (i, shapes[i])
+        n_inner = ws[i][0].numel()
+        # same per-element arithmetic; the per-channel means differ in summation order (1e-5 on gx),
+        # the zero-point gradient that lands on the row minimum is a difference of two O(N) sums
+        flat = ws[i].reshape(shapes[i][0], -1)
+        ties = ((flat == flat.amin(1, keepdim=True)) | (flat == flat.amax(1, keepdim=True))).reshape(shapes[i]).cpu()
+        a, b = W[i].grad.cpu(), gw_r.cpu()
+        H.assert_close_rel(a[~ties], b[~ties], REL, f"g_w[{i}]", abs_floor=1e-7)
+        H.assert_close_rel(a[ties], b[ties], REL, f"g_w[{i}] (row extrema)", abs_floor=max(2e-5, 1.5e-6 * math.sqrt(n_inner)))
+        H.assert_close_rel(L[i].grad, gls_r, REL, f"g_log_s[{i}]", abs_floor=4e-7 * math.sqrt(n_inner) + 1e-7)
