@@ -314,37 +314,6 @@ def qat_leg(a, dev, world, rank, use_dist, spec, ref_flags=False, profile_share=
 
     res = {}
     k = a.resnet_steps
-    if graph and not use_dist:
-        # the same step launched eagerly from Python first: its time, and (CUPTI) which share of
-        # the GPU time the fake-quant kernels take — a graph replay hides kernel names from CUPTI
-        for _ in range(4):
-            eager_step()
-        res["eager_ms_per_step"] = round(time_region(eager_step, k, False) / k, 2)
-    if rank == 0 and not use_dist and profile_share:   # (a rank-local DDP step would dead-lock the other ranks)
-        try:
-            from torch.profiler import profile, ProfilerActivity
-            eager_step()
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                eager_step(); eager_step()
-                torch.cuda.synchronize()
-            tot = fq = 0.0
-            nl = nfq = 0
-            for ev in prof.key_averages():
-                dt = getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0)
-                tot += dt
-                nl += ev.count
-                if "fq_" in ev.key:
-                    fq += dt
-                    nfq += ev.count
-            if tot > 0:
-                res["fake_quant_kernel_share"] = round(fq / tot, 4)
-                res["fake_quant_ms_per_step"] = round(fq / 2 / 1e3, 3)
-                res["gpu_kernel_ms_per_step"] = round(tot / 2 / 1e3, 2)   # rest of an eager step = GPU idle
-                res["launches_per_step"] = nl // 2
-                res["fake_quant_launches_per_step"] = nfq // 2
-        except Exception as exc:   # profiler unavailable: the throughput numbers stand alone
-            res["fake_quant_kernel_share"] = None
-            res["profiler_error"] = str(exc)[:80]
     if use_dist and method == "AEWGS":
         # the ONE data-path collective (gdnsq.py:126-129, here one packed all-reduce per weight
         # tensor): its GPU time per step, CUDA events around every call over 3 eager DDP steps
@@ -375,6 +344,8 @@ def qat_leg(a, dev, world, rank, use_dist, spec, ref_flags=False, profile_share=
                                                 "recorded right before and after the call in eager DDP steps: NCCL launch + "
                                                 "transfer + waiting for the slowest rank to reach this point of its backward"}
 
+    # The headline (graph-replayed step) is measured FIRST, on a GPU that has not yet been pushed
+    # into its power cap by the eager / profiler passes below (sustained load lowers the SM clock).
     graphed = None
     if graph:
         # capture; if it fails on ANY rank every rank falls back to eager launches (the bench
@@ -419,6 +390,45 @@ def qat_leg(a, dev, world, rank, use_dist, spec, ref_flags=False, profile_share=
     ke = max(3, k // 2)
     step_e2e()
     ms_e = time_region(step_e2e, ke, use_dist) / ke
+    if graphed is not None:
+        graphed.close()
+        graphed = None
+        graph_was_used = True
+        torch.cuda.synchronize()
+        opt = q.configure_optimizers()
+    else:
+        graph_was_used = False
+    if graph and not use_dist:
+        # the same step launched eagerly from Python first: its time, and (CUPTI) which share of
+        # the GPU time the fake-quant kernels take — a graph replay hides kernel names from CUPTI
+        for _ in range(4):
+            eager_step()
+        res["eager_ms_per_step"] = round(time_region(eager_step, k, False) / k, 2)
+    if rank == 0 and not use_dist and profile_share:   # (a rank-local DDP step would dead-lock the other ranks)
+        try:
+            from torch.profiler import profile, ProfilerActivity
+            eager_step()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                eager_step(); eager_step()
+                torch.cuda.synchronize()
+            tot = fq = 0.0
+            nl = nfq = 0
+            for ev in prof.key_averages():
+                dt = getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0)
+                tot += dt
+                nl += ev.count
+                if "fq_" in ev.key:
+                    fq += dt
+                    nfq += ev.count
+            if tot > 0:
+                res["fake_quant_kernel_share"] = round(fq / tot, 4)
+                res["fake_quant_ms_per_step"] = round(fq / 2 / 1e3, 3)
+                res["gpu_kernel_ms_per_step"] = round(tot / 2 / 1e3, 2)   # rest of an eager step = GPU idle
+                res["launches_per_step"] = nl // 2
+                res["fake_quant_launches_per_step"] = nfq // 2
+        except Exception as exc:   # profiler unavailable: the throughput numbers stand alone
+            res["fake_quant_kernel_share"] = None
+            res["profiler_error"] = str(exc)[:80]
     cfg = {"resnet18": "configs[3] ResNet-18 224x224", "resnet20": "configs[2] ResNet-20 32x32 (CIFAR-100 shaped)",
            "rfdn": "configs[4] RFDN x4 SR, 256x256 LR patches, L1"}[model_name]
     par = "single GPU"
@@ -427,7 +437,7 @@ def qat_leg(a, dev, world, rank, use_dist, spec, ref_flags=False, profile_share=
                                   "broadcast" if ref_flags else ", lean wrapping (log_b_s ignored, no buffer broadcast)")
     res = {"workload": f"{cfg} {method} W{bits}A{bits} QAT, {'no teacher' if sr else 'distillation'}, RAdam, fp32/TF32, "
                        f"batch {B}/GPU, {'channels_last' if a.channels_last else 'NCHW'}, {par}, "
-                       f"{'whole step (NCCL all-reduces included) replayed from a CUDA graph' if graphed is not None else 'eager launches'}",
+                       f"{'whole step (NCCL all-reduces included) replayed from a CUDA graph' if graph_was_used else 'eager launches'}",
            "img_per_s": round(world * B / (ms * 1e-3), 1), "ms_per_step": round(ms, 2),
            "e2e_img_per_s": round(world * B / (ms_e * 1e-3), 1),
            "e2e_h2d_bytes_per_step": hx.numel() * hx.element_size() + ht.numel() * ht.element_size(),
@@ -442,8 +452,6 @@ def qat_leg(a, dev, world, rank, use_dist, spec, ref_flags=False, profile_share=
         lo_, hi_ = chk.clone(), chk.clone()
         dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
         res["ddp_replicas_in_sync"] = bool((lo_ == hi_).item())
-    if graphed is not None:
-        graphed.close()
     del q, graphed, step, feed
     torch.cuda.empty_cache()
     return res
