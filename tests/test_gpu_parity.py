@@ -318,7 +318,7 @@ def test_deterministic(fq):
 # full-size checks (BASELINE config 2): the oracle's ATen chain runs on the GPU
 # itself as the checker; plus size-independent properties
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("log2n,bits", [(26, 4), (28, 8)])
+@pytest.mark.parametrize("log2n,bits", [(26, 4), (28, 8), (30, 4)])     # flat kernel (<= 2^28) and streaming (2^30)
 def test_full_size_vs_oracle_on_device(fq, log2n, bits):
     n = 1 << log2n
     g = torch.Generator(device="cuda").manual_seed(0)
