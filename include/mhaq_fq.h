@@ -99,10 +99,13 @@ const char *mhaq_fq_build_info(void);
 
 /* Workspaces (caller-owned device memory) for a [n_rows][n_inner] tensor:
  *   ws      : mhaq_fq_workspace_bytes() bytes of scratch, contents irrelevant.
- *   tickets : mhaq_fq_ticket_count() unsigned ints used by the deterministic finalize.
- *             They MUST be zero on entry; the kernel leaves them zero again, so one
- *             zero-initialised buffer can be reused forever by calls that are ordered on
- *             one stream (allocate one per stream).
+ *   tickets : mhaq_fq_ticket_count() unsigned ints, 16-byte aligned, used by the deterministic
+ *             reductions: one ticket per channel for the finalize, followed by the region in
+ *             which the single-launch per-tensor backward hands its per-block records to the
+ *             summing block (every 64-bit word doubles as its own "ready" flag: zero = not
+ *             written).  The buffer MUST be zero on entry; every launch leaves it zero
+ *             again, so one zero-initialised buffer can be reused forever by calls that are
+ *             ordered on one stream (allocate one per stream).
  * mhaq_fq_num_tasks: number of records the streaming kernels write (informational). */
 int64_t mhaq_fq_num_tasks(int64_t n_rows, int64_t n_inner);
 int64_t mhaq_fq_workspace_bytes(int64_t n_rows, int64_t n_inner);
@@ -167,8 +170,9 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets,
  * STE / LSQ estimator, gradient w.r.t. y and at most 2^28 elements it is ONE kernel: a
  * persistent, balanced grid (<= SMs x 4 blocks; operands staged through a TMA bulk-copy ring;
  * each block one contiguous range, or — from 2^24 elements — every grid-th 8 Ki-element chunk)
- * whose last block to finish (ticket) sums the per-block fp64 records in index order and writes
- * the gradients — no second launch, no per-task flushes; bitwise reproducible on a given device.
+ * whose block 0 sums the per-block fp64 records in index order (handed over through
+ * self-validating words in `tickets`: no fence, no atomic) and writes the gradients — no second
+ * launch, no per-task flushes; bitwise reproducible on a given device.
  * Everything else runs the two launches above.  mhaq_fq_bwd_single_launch() tells which (for
  * 16-byte aligned operands). */
 int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx,

@@ -775,12 +775,11 @@ fq_bwd_kernel(const float *__restrict__ go, const float *__restrict__ x, float *
 // the contiguous range of `per_cta` 2048-element batches [b*per_cta, ...) — every block resident at
 // once with (almost) the same amount of work, no waves — folds its fp32 per-thread partials into
 // per-warp fp64 accumulators every 4 batches (64 elements per thread, like a 2-sub-tile task of
-// the streaming kernel), writes ONE record, and the last block to finish (ticket) sums the
-// <= cap records in index order and applies emit_param_grads.  Deterministic: the partition and
-// both summation orders are functions of the shape only; the ticket decides who sums, not how.
+// the streaming kernel), publishes ONE self-validating record, and block 0 sums the <= cap
+// records in index order and applies emit_param_grads.  Deterministic: the partition and both
+// summation orders are functions of the shape only.
 // The noise stream is the streaming kernel's (a function of the element position only).
-// The release fence that made an in-kernel reduction unattractive per 8 Ki-element task
-//  is paid once per CTA lifetime here.
+// No fence, no atomic: the record words are their own "ready" flags (see flat_enc below).
 constexpr int kBatchElems = kIterElems * kU;      // 2048
 constexpr int kFlatGroup = 4;                     // batches between fp32 -> fp64 folds
 constexpr int kFlatCapMax = 2048;                 // upper bound on the grid (workspace sizing)
@@ -868,18 +867,44 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// ---- per-block records of the flat backward, published without fence or ticket ----
+// A record is 3 x 16 bytes {v0,v1} {v2,v3} {v4,1}; every 64-bit word is stored ENCODED so that it
+// is never zero (bits(v + 0.0) ^ sign bit: +0.0 -> 0x8000..., -0.0 cannot occur after "+ 0.0"),
+// and zero means "not written yet".  The reader (block 0) polls the words
+// themselves, so no ordering between data and a flag is needed — the data IS the flag — and
+// writes zero back after it has read a record (the region lives in the zero-initialised ticket
+// buffer, which every launch leaves zero: include/mhaq_fq.h).
+constexpr int kFlatRecWords = 6;                  // 64-bit words per record (48 bytes)
+constexpr int kFlatRecOffsetU32 = 4;              // records start 16 bytes into the ticket buffer
+__device__ __forceinline__ unsigned long long flat_enc(double v) {
+    return (unsigned long long)__double_as_longlong(v + 0.0) ^ 0x8000000000000000ull;
+}
+__device__ __forceinline__ double flat_dec(unsigned long long b) {
+    return __longlong_as_double((long long)(b ^ 0x8000000000000000ull));
+}
+__device__ __forceinline__ void st_rec2(unsigned long long *p, unsigned long long a, unsigned long long b) {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_rec2(const unsigned long long *p, unsigned long long &a, unsigned long long &b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
 // operand staging ring: kFlatStages x (8 KB x + 8 KB go) per CTA (dynamic shared memory)
@@ -912,10 +937,9 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
     extern __shared__ __align__(128) unsigned char flat_smem[];
     float *const s_x = reinterpret_cast<float *>(flat_smem);                   // [stages][2048]
     float *const s_g = s_x + kFlatStages * kBatchElems;                         // [stages][2048]
-    __shared__ __align__(8) uint64_t s_bar[kFlatStages];
+    __shared__ __align__(8) uint64_t s_bar[kFlatStages];      // the stage's bytes have landed
     __shared__ double s_acc[5][kThreads / 32];
     __shared__ double s_fin[5][kFinThreads / 32];
-    __shared__ int s_last;
     constexpr uint32_t kOpBytes = kBatchElems * sizeof(float);   // 8192
     const int64_t b0 = (int64_t)blockIdx.x * f.k;
     int nb;                                                       // batches of this block
@@ -951,6 +975,10 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
             for (int i = 0; i < kFlatStages && i < nb; ++i) issue(i);
         }
         if (nb > 0) __syncthreads();                              // the mbarriers are initialised
+        // (Releasing a stage through an "empty" mbarrier as soon as the four warps have copied it
+        // to registers — two batches in flight during every compute phase — was measured: neutral
+        // below 2^24 elements, 15-18 % SLOWER above, like a third stage or a fifth block per SM:
+        // more requests in flight break up the moving band of DRAM pages.  profiles/r02_midsize.md)
         for (int i = 0; i < nb; ++i) {
             __syncthreads();
             if (tid == kThreads && i >= 1 && i - 1 + kFlatStages < nb) issue(i - 1 + kFlatStages);
@@ -1113,32 +1141,82 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
     // parameter gradients are then NOT produced; never set in production)
     if (exp_flags & 1) return;
     __syncthreads();
-    if (tid == kThreads) {
-        double *rec = ws + (int64_t)blockIdx.x * kNPart;
+    // ---- records without fence or ticket: every block but block 0 stores its encoded record and
+    // leaves; block 0 polls the record words until they are non-zero, sums them in index order
+    // (thread t takes records t, t + 160, ...) and writes zero back.  One store -> load hand-over
+    // on the critical path instead of store, fence, atomic, load: 1.6-1.9 us less per call
+    // (profiles/r02_midsize.md).  Block 0 owns a full share of the work, so it starts polling
+    // when the other blocks are finishing too: a reader that polls EARLY (the last block, which
+    // owns the short remainder, was tried) pulls the record lines towards itself and slows the
+    // hand-over down (+4 us at 12.8 M elements).  The grid is at most SMs x 4 blocks, all
+    // resident together; were it ever not, block 0 holds one slot while every other block runs
+    // to completion, so the wait ends — and a bounded spin traps instead of hanging.
+    unsigned long long *recs = reinterpret_cast<unsigned long long *>(ticket + kFlatRecOffsetU32);
+    const int last = (int)gridDim.x - 1;
+    constexpr int reader = 0;
+    if ((int)blockIdx.x != reader) {
+        if (tid == kThreads) {
+            double v[5];
 #pragma unroll
-        for (int m = 0; m < 5; ++m) {
-            double a = 0.0;
+            for (int m = 0; m < 5; ++m) {
+                double a = 0.0;
 #pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) a += s_acc[m][w];
-            rec[m] = a;
+                for (int w = 0; w < kThreads / 32; ++w) a += s_acc[m][w];
+                v[m] = a;
+            }
+            unsigned long long *rec = recs + (int64_t)blockIdx.x * kFlatRecWords;
+            st_rec2(rec + 0, flat_enc(v[0]), flat_enc(v[1]));
+            st_rec2(rec + 2, flat_enc(v[2]), flat_enc(v[3]));
+            st_rec2(rec + 4, flat_enc(v[4]), 1ull);
         }
-        __threadfence();                                     // record visible before the ticket
-        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+        return;
     }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
     double a[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int i = tid; i < (int)gridDim.x; i += kFlatThreads) {
-        const double *rec = ws + (int64_t)i * kNPart;
+    constexpr int kPerThread = (kFlatCapMax + kFlatThreads - 1) / kFlatThreads;
+    for (int k0 = 0; k0 < kPerThread; k0 += 4) {
+        if (tid + k0 * kFlatThreads > last) break;
+        unsigned long long w[4][kFlatRecWords];
+        // first pass: all loads of up to 4 records in flight at once
 #pragma unroll
-        for (int m = 0; m < 5; ++m) a[m] += __ldcg(rec + m);
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + (k0 + k) * kFlatThreads;
+            if (i <= last && i != reader) {
+                const unsigned long long *rec = recs + (int64_t)i * kFlatRecWords;
+                ld_rec2(rec + 0, w[k][0], w[k][1]);
+                ld_rec2(rec + 2, w[k][2], w[k][3]);
+                ld_rec2(rec + 4, w[k][4], w[k][5]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + (k0 + k) * kFlatThreads;
+            if (i <= last && i != reader) {
+                unsigned long long *rec = recs + (int64_t)i * kFlatRecWords;
+                unsigned int spins = 0;
+                while (!(w[k][0] && w[k][1] && w[k][2] && w[k][3] && w[k][4] && w[k][5])) {
+                    if (++spins > (1u << 24)) __trap();      // a lost block: fail loudly, never hang
+                    ld_rec2(rec + 0, w[k][0], w[k][1]);
+                    ld_rec2(rec + 2, w[k][2], w[k][3]);
+                    ld_rec2(rec + 4, w[k][4], w[k][5]);
+                }
+                st_rec2(rec + 0, 0ull, 0ull);                // leave the region zero for the next launch
+                st_rec2(rec + 2, 0ull, 0ull);
+                st_rec2(rec + 4, 0ull, 0ull);
+#pragma unroll
+                for (int m = 0; m < 5; ++m) a[m] += flat_dec(w[k][m]);
+            } else if (i == reader) {                        // this block's own record: from shared memory
+#pragma unroll
+                for (int m = 0; m < 5; ++m) {
+                    double b = 0.0;
+#pragma unroll
+                    for (int ww = 0; ww < kThreads / 32; ++ww) b += s_acc[m][ww];
+                    a[m] += b;
+                }
+            }
+        }
     }
     block_sum_cols<5>(a, s_fin);
-    if (tid == 0) {
-        emit_param_grads(prm, 0, a, o0, o1, o2, o3);
-        *ticket = 0u;
-    }
+    if (tid == 0) emit_param_grads(prm, 0, a, o0, o1, o2, o3);
 }
 
 // ===========================================================================
@@ -1624,7 +1702,8 @@ int64_t mhaq_fq_workspace_bytes(int64_t n_rows, int64_t n_inner) {
 
 int64_t mhaq_fq_ticket_count(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
     (void)n_rows; (void)n_inner;
-    return n_ch > 0 ? n_ch : 1;
+    // per-channel tickets, then (16-byte aligned) the flat backward's self-validating records
+    return (n_ch > 0 ? n_ch : 1) + kFlatRecOffsetU32 + (int64_t)kFlatCapMax * kFlatRecWords * 2;
 }
 
 int mhaq_fq_fwd_f32(const float *x, float *y, float *codes, const float *scale, const float *zp,

@@ -190,6 +190,7 @@ def _workspace(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
 # training path allocates nothing per call.  Bounded: the least recently used stream's entry is
 # dropped beyond _ARENA_MAX streams.
 _ARENA_MAX = 16
+_FLAT_REC_U32 = 4 + 2048 * 12          # include/mhaq_fq.h: mhaq_fq_ticket_count
 _arenas = {}
 
 
@@ -214,11 +215,12 @@ def _arena(x: torch.Tensor) -> _Arena:
 
 
 def _tickets(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
-    need = geo.n_ch if geo.n_ch > 0 else 1       # == mhaq_fq_ticket_count
+    # == mhaq_fq_ticket_count: per-channel tickets + the flat backward's record region
+    need = (geo.n_ch if geo.n_ch > 0 else 1) + _FLAT_REC_U32
     a = _arena(x)
     buf = a.tickets
     if buf is None or buf.numel() < need:
-        n = max(4096, 1 << (int(need) - 1).bit_length())
+        n = max(32768, 1 << (int(need) - 1).bit_length())
         buf = a.tickets = torch.zeros(n, dtype=torch.int32, device=x.device)
     return buf
 

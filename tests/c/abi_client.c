@@ -21,7 +21,7 @@ int main(void) {
     CHECK(mhaq_fq_build_info() != NULL);
     CHECK(mhaq_fq_num_tasks(1, 4097) == 2);
     CHECK(mhaq_fq_workspace_bytes(4, 1000) >= 4 * 8 * (int64_t)sizeof(double));
-    CHECK(mhaq_fq_ticket_count(64, 576, 64) == 64);
+    CHECK(mhaq_fq_ticket_count(64, 576, 64) == 64 + 4 + 2048 * 12);
     /* argument errors are reported before anything touches CUDA */
     CHECK(mhaq_fq_fwd_f32(NULL, dummy, NULL, dummy, dummy, NULL, NULL, 0, 0, 0, 0,
                           MHAQ_FQ_PARAMS_LINEAR, 1, 4, 1, NULL, NULL) == MHAQ_FQ_ENULL);

@@ -41,9 +41,10 @@ def test_geometry_is_a_pure_function_of_shape():
     assert L.mhaq_fq_num_tasks(0, 10) == 0
     # streaming kernels: one task per 4096-element sub-tile
     assert L.mhaq_fq_num_tasks(1, 1 << 30) == 1 << 18
-    # one finalize ticket per channel
-    assert L.mhaq_fq_ticket_count(1, 1 << 30, 1) == 1
-    assert L.mhaq_fq_ticket_count(512, 4608, 512) == 512
+    # one finalize ticket per channel + the flat backward's record region (4 + 2048 x 12 words)
+    flat = 4 + 2048 * 12
+    assert L.mhaq_fq_ticket_count(1, 1 << 30, 1) == 1 + flat
+    assert L.mhaq_fq_ticket_count(512, 4608, 512) == 512 + flat
     assert L.mhaq_fq_workspace_bytes(1, 1 << 30) >= (1 << 18) * 8 * 8
 
 

@@ -314,6 +314,71 @@ def test_deterministic(fq):
             assert torch.equal(a, b)
 
 
+def test_flat_backward_record_handover_is_stateless(fq):
+    """The single-launch per-tensor backward hands its per-block records to block 0 through
+    self-validating words in the stream's ticket buffer (include/mhaq_fq.h).  Back-to-back
+    launches of different sizes (different grids, so different record counts) on one stream, then
+    replays of one captured launch: every result equals the first run of that size bit for bit,
+    and the buffer is zero again after every launch."""
+    from mhaq_b200 import ops
+    sizes = [2048 * 9, 6422528, 2048 * 592 * 3 + 2048 * 7 + 4, 4 << 20, 2044, 1 << 24, 12845056]
+    b = torch.tensor([-2.0], device="cuda")
+    s = torch.tensor([0.25], device="cuda")
+    hi = b + 4.0 - s
+    data = {}
+    for n in sizes:
+        g = torch.Generator(device="cuda").manual_seed(n % 1009)
+        data[n] = (torch.randn(n, device="cuda", generator=g) * 1.5, torch.randn(n, device="cuda", generator=g))
+
+    def run(n):
+        x, go = data[n]
+        assert ops.lib.mhaq_fq_bwd_single_launch(1, n, 1, 0, 0) == 1
+        xs = x.clone().requires_grad_(True)
+        s_, b_, h_ = (t.clone().requires_grad_(True) for t in (s, b, hi))
+        fq.fake_quant(xs, s_, b_, b_, h_, method="STE", philox=(3, 4)).backward(go)
+        return xs.grad, s_.grad, b_.grad, h_.grad
+
+    first = {n: run(n) for n in sizes}
+    for rep in range(3):
+        for n in sizes[::-1] if rep % 2 else sizes:
+            for a, c in zip(first[n], run(n)):
+                assert torch.equal(a, c), (n, rep)
+    torch.cuda.synchronize()
+    tk = ops._arena(data[sizes[0]][0]).tickets
+    assert tk is not None and bool((tk == 0).all()), "the ticket / record buffer must be left zero"
+
+    # one captured launch replayed many times (the training step's situation)
+    n = 6422528
+    x, go = data[n]
+    L = ops._Launch(x, s, b, b, hi)
+    gx = torch.empty_like(x)
+    out = torch.zeros(4, 1, device="cuda")
+    ws = ops._workspace(x, L.geo)
+    tk2 = torch.zeros(1 + 4 + 2048 * 12, dtype=torch.int32, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+
+    def launch():
+        ops.check(ops.lib.mhaq_fq_bwd_fused_f32(
+            go.data_ptr(), x.data_ptr(), gx.data_ptr(), *L.params(), 1, n, 1, 0, 0, None, 3, 4, None, None,
+            ws.data_ptr(), tk2.data_ptr(), out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+            out[3].data_ptr(), ops._stream()), "bwd_fused")
+    with torch.cuda.stream(side):
+        launch()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        launch()
+    for _ in range(50):
+        out.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(gx, first[n][0])
+        assert torch.equal(out[0], first[n][1]) and torch.equal(out[3], first[n][3])
+    assert bool((tk2 == 0).all())
+
+
 # ---------------------------------------------------------------------------
 # full-size checks (BASELINE config 2): the oracle's ATen chain runs on the GPU
 # itself as the checker; plus size-independent properties

@@ -1,0 +1,13 @@
+#!/bin/bash
+# flat backward v2 diagnosis: which of {ring release (S), polled records (P), reader block (R)} costs what, at which size
+E=/root/repo/tools/_exp
+for lib in s0p0 s1p0 s0p1r0 s0p1r1 s1p1r0; do
+  for mode in quick large; do
+    echo "== $mode: $lib"
+    MHAQ_FQ_LIB=$E/libmhaq_fq_$lib.so timeout 300 python tools/midsize_graph.py --$mode --out gpurun_out/tmp_exp.json 2>&1
+  done
+done
+for lib in s0p1r0 s0p1r1; do
+  echo "== large, epilogue skipped: $lib"
+  MHAQ_FQ_FLAT_EXP=1 MHAQ_FQ_LIB=$E/libmhaq_fq_$lib.so timeout 300 python tools/midsize_graph.py --large --out gpurun_out/tmp_exp.json 2>&1
+done
