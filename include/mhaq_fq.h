@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define MHAQ_FQ_ABI_VERSION 5
+#define MHAQ_FQ_ABI_VERSION 6
 
 /* gradient estimators — numeric values follow the reference enum
  * QNMethod (src/quantization/gdnsq/gdnsq_utils.py:9-13). */
@@ -110,6 +110,11 @@ const char *mhaq_fq_build_info(void);
 int64_t mhaq_fq_num_tasks(int64_t n_rows, int64_t n_inner);
 int64_t mhaq_fq_workspace_bytes(int64_t n_rows, int64_t n_inner);
 int64_t mhaq_fq_ticket_count(int64_t n_rows, int64_t n_inner, int64_t n_ch);
+/* Id of the CUDA-graph capture `stream` is currently recording into, 0 when it is not capturing
+ * (cudaStreamGetCaptureInfo).  A host layer that keeps one ticket buffer per stream uses it to
+ * give every capture its own buffer: a graph may later be replayed on any stream, concurrently
+ * with eager launches on the stream it was captured from. */
+unsigned long long mhaq_fq_stream_capture_id(void *stream);
 
 /* Forward: y = rint((clamp(x,lo,hi) - zp) / s) * s + zp, each step one IEEE
  * fp32 rounding (no FMA contraction, true division, round-half-even).

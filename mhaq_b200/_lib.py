@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MHAQ_FQ_LIB: experiment knob to load an alternative build of the same ABI
 LIB_PATH = os.environ.get("MHAQ_FQ_LIB") or os.path.join(_HERE, "csrc", "libmhaq_fq.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 NPART = 8  # MHAQ_FQ_NPART
 
 class WRowFwdDesc(ctypes.Structure):
@@ -38,6 +38,7 @@ _SIGNATURES = {
     "mhaq_fq_num_tasks": (c_int64, [c_int64, c_int64]),
     "mhaq_fq_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "mhaq_fq_ticket_count": (c_int64, [c_int64, c_int64, c_int64]),
+    "mhaq_fq_stream_capture_id": (c_uint64, [_P]),
     "mhaq_fq_fwd_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                 c_int64, c_int64, c_int64, _P, _P]),
     "mhaq_fq_minmax_finalize": (c_int, [_P, c_int64, c_int64, _P, _P]),

@@ -1676,6 +1676,16 @@ extern "C" {
 
 int mhaq_fq_abi_version(void) { return MHAQ_FQ_ABI_VERSION; }
 
+unsigned long long mhaq_fq_stream_capture_id(void *stream) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo((cudaStream_t)stream, &status, &id) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return status == cudaStreamCaptureStatusActive ? id : 0;
+}
+
 const char *mhaq_fq_build_info(void) {
     return "mhaq_fq sm_100a fp32 fake-quant; cuda " __DATE__ " " __TIME__;
 }

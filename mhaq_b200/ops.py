@@ -184,7 +184,7 @@ def _workspace(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
     return torch.empty(_ws_bytes(geo) // 8, dtype=torch.float64, device=x.device)
 
 
-# Per-(device, stream) scratch of the backward pass.  Calls ordered on one stream may share
+# Per-(device, stream[, graph capture]) scratch of the backward pass.  Calls ordered on one stream may share
 # the record workspace (kernel k+1 writes it after finalize k has read it) and the ticket
 # counters (zero on entry, restored to zero by the kernel: include/mhaq_fq.h), so the eager
 # training path allocates nothing per call.  Bounded: the least recently used stream's entry is
@@ -203,7 +203,13 @@ class _Arena:
 
 
 def _arena(x: torch.Tensor) -> _Arena:
-    key = (x.device.index, torch._C._cuda_getCurrentRawStream(x.device.index))
+    raw = torch._C._cuda_getCurrentRawStream(x.device.index)
+    # A capture gets an arena of its own (key: the capture id): the graph may be replayed on any
+    # stream later, concurrently with eager launches on the stream it was captured from, so its
+    # ticket buffer must not be the stream's.  (Its zero-fill is captured once per graph; the
+    # memory comes from the graph's private pool and stays reserved for the graph's lifetime.)
+    cap = int(lib.mhaq_fq_stream_capture_id(raw)) if torch.cuda.is_current_stream_capturing() else 0
+    key = (x.device.index, raw, cap)
     a = _arenas.get(key)
     if a is None:
         if len(_arenas) >= _ARENA_MAX:
@@ -226,10 +232,8 @@ def _tickets(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
 
 
 def _shared_workspace(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
-    """The stream's reusable record workspace; a private buffer while a CUDA graph is being
-    captured (a captured call must not alias scratch that eager calls keep using)."""
-    if torch.cuda.is_current_stream_capturing():
-        return _workspace(x, geo)
+    """The stream's reusable record workspace (a CUDA-graph capture has an arena of its own, so a
+    captured call never aliases scratch that eager calls keep using)."""
     need = _ws_bytes(geo) // 8
     a = _arena(x)
     buf = a.ws

@@ -379,6 +379,48 @@ def test_flat_backward_record_handover_is_stateless(fq):
     assert bool((tk2 == 0).all())
 
 
+def test_graph_capture_gets_its_own_scratch_arena(fq):
+    """A captured backward must not share the ticket / record buffer of the stream it was captured
+    from: the graph is replayed on the default stream here while eager calls keep running on a
+    side stream, concurrently.  Both keep producing the eager result bit for bit."""
+    from mhaq_b200 import ops
+    n = 6422528
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(n, device="cuda", generator=g) * 1.5
+    go = torch.randn(n, device="cuda", generator=g)
+    b = torch.tensor([-2.0], device="cuda")
+    s = torch.tensor([0.25], device="cuda")
+    hi = b + 4.0 - s
+
+    def run():
+        xs = x.clone().requires_grad_(True)
+        s_, b_, h_ = (t.clone().requires_grad_(True) for t in (s, b, hi))
+        y = fq.fake_quant(xs, s_, b_, b_, h_, method="STE", philox=(3, 4))
+        return torch.autograd.grad(y, (xs, s_, b_, h_), go)
+
+    want = run()
+    torch.cuda.synchronize()
+    sx = x.clone().requires_grad_(True)
+    sp = [t.clone().requires_grad_(True) for t in (s, b, hi)]
+    before = set(ops._arenas)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y = fq.fake_quant(sx, sp[0], sp[1], sp[1], sp[2], method="STE", philox=(3, 4))
+        got = torch.autograd.grad(y, (sx, sp[0], sp[1], sp[2]), go)
+    new = [k for k in set(ops._arenas) - before if k[2] != 0]
+    assert new, "the capture did not get an arena keyed by its capture id"
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    for _ in range(25):
+        graph.replay()
+        with torch.cuda.stream(side):
+            eager = run()
+        torch.cuda.synchronize()
+        for a, c, e in zip(want, got, eager):
+            assert torch.equal(a, c), "graph replay"
+            assert torch.equal(a, e), "eager call next to the replay"
+
+
 # ---------------------------------------------------------------------------
 # full-size checks (BASELINE config 2): the oracle's ATen chain runs on the GPU
 # itself as the checker; plus size-independent properties
