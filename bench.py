@@ -415,6 +415,8 @@ def qat_leg(a, dev, world, rank, use_dist, spec, ref_flags=False, profile_share=
             nl = nfq = 0
             for ev in prof.key_averages():
                 dt = getattr(ev, "device_time_total", 0.0) or getattr(ev, "cuda_time_total", 0.0)
+                if dt <= 0:
+                    continue                 # host-side runtime-API records: not GPU work
                 tot += dt
                 nl += ev.count
                 if "fq_" in ev.key:
