@@ -172,7 +172,7 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets,
 
 /* mhaq_fq_bwd_f32 + mhaq_fq_bwd_finalize_f32 as one entry point (same arguments, the union of
  * the two lists).  For a per-tensor tensor (n_rows = n_ch = 1: every activation) with the
- * STE / LSQ estimator, gradient w.r.t. y and at most 2^28 elements it is ONE kernel: a
+ * STE / LSQ estimator and the gradient w.r.t. y it is ONE kernel: a
  * persistent, balanced grid (<= SMs x 4 blocks; operands staged through a TMA bulk-copy ring;
  * each block one contiguous range, or — from 2^24 elements — every grid-th 8 Ki-element chunk)
  * whose block 0 sums the per-block fp64 records in index order (handed over through

@@ -884,6 +884,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // ---- per-block records of the flat backward, published without fence or ticket ----
 // A record is 3 x 16 bytes {v0,v1} {v2,v3} {v4,1}; every 64-bit word is stored ENCODED so that it
@@ -920,7 +923,7 @@ constexpr int kFlatThreads = kThreads + 32;
 constexpr int kFlatSmemBytes = kFlatStages * 2 * kBatchElems * (int)sizeof(float);
 constexpr int kFlatCtasPerSm = 4;
 
-template <int METHOD, bool CLAMP, int NOISE>
+template <int METHOD, bool CLAMP, int NOISE, bool MBAR>
 __global__ void __launch_bounds__(kFlatThreads, kFlatCtasPerSm)
 fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, float *__restrict__ gx,
                    QParams prm, FlatGeom f, const float *__restrict__ r, uint64_t seed,
@@ -938,6 +941,7 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
     float *const s_x = reinterpret_cast<float *>(flat_smem);                   // [stages][2048]
     float *const s_g = s_x + kFlatStages * kBatchElems;                         // [stages][2048]
     __shared__ __align__(8) uint64_t s_bar[kFlatStages];      // the stage's bytes have landed
+    __shared__ __align__(8) uint64_t s_emp[kFlatStages];      // MBAR: all 4 compute warps have copied it to registers
     __shared__ double s_acc[5][kThreads / 32];
     __shared__ double s_fin[5][kFinThreads / 32];
     constexpr uint32_t kOpBytes = kBatchElems * sizeof(float);   // 8192
@@ -970,7 +974,10 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
         // compute of batch i-1 when it arrives at the barrier of iteration i)
         if (tid == kThreads && nb > 0) {
 #pragma unroll
-            for (int sg = 0; sg < kFlatStages; ++sg) mbar_init(&s_bar[sg], 1);
+            for (int sg = 0; sg < kFlatStages; ++sg) {
+                mbar_init(&s_bar[sg], 1);
+                if (MBAR) mbar_init(&s_emp[sg], kThreads / 32);
+            }
             mbar_fence_init();
             for (int i = 0; i < kFlatStages && i < nb; ++i) issue(i);
         }
@@ -979,9 +986,23 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
         // to registers — two batches in flight during every compute phase — was measured: neutral
         // below 2^24 elements, 15-18 % SLOWER above, like a third stage or a fifth block per SM:
         // more requests in flight break up the moving band of DRAM pages.  profiles/r02_midsize.md)
-        for (int i = 0; i < nb; ++i) {
-            __syncthreads();
-            if (tid == kThreads && i >= 1 && i - 1 + kFlatStages < nb) issue(i - 1 + kFlatStages);
+        // Refill point: batch i+1 is issued once every compute warp has READ batch i (so exactly one
+        // batch is in flight during a compute phase).  Two ways to learn that, chosen by size:
+        //   block barrier per batch            — best below 2^26 elements (short kernels)
+        //   "empty" mbarrier, warps never wait — 3 % faster from 2^27 (478 vs 495 us at 2^28),
+        //     for each other (MBAR)              0.3-1.5 us slower below 2^26 (r02_exp_flat5.txt)
+        if (MBAR) {
+            if (tid == kThreads)
+                for (int i = 1; i - 1 + kFlatStages < nb; ++i) {
+                    mbar_wait(&s_emp[i % kFlatStages], (uint32_t)(i / kFlatStages) & 1u);
+                    issue(i - 1 + kFlatStages);
+                }
+            __syncwarp();
+        } else {
+            for (int i = 0; i < nb; ++i) {
+                __syncthreads();
+                if (tid == kThreads && i >= 1 && i - 1 + kFlatStages < nb) issue(i - 1 + kFlatStages);
+            }
         }
     } else {
     if ((tid & 31) == 0) {
@@ -1089,14 +1110,18 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
             rv4[u] = (NOISE == NOISE_EXPLICIT) ? ld_stream4(r + base + u * kIterElems)
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        // every thread is past the compute of batch i-1 here: the auxiliary warp refills that
-        // batch's stage behind this barrier
-        __syncthreads();
+        // (!MBAR) every thread is past the compute of batch i-1 here: the auxiliary warp refills
+        // that batch's stage behind this barrier
+        if (!MBAR) __syncthreads();
         if (fast_ok) {
             uint32_t mn = 0xffffffffu;
 #pragma unroll
             for (int u = 0; u < kU; ++u) mn = nzmin4(mn, gv[u]);
             const bool odd = mn < kGoLoBits2m1;
+            if (MBAR) {      // the staged operands are in registers (mn depends on the last load issued)
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&s_emp[st]);
+            }
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
                 const int64_t p = base + u * kIterElems;
@@ -1128,6 +1153,10 @@ fq_bwd_flat_kernel(const float *__restrict__ go, const float *__restrict__ x, fl
                 o.z = bwd_elem<METHOD, CLAMP, NOISE, false, false>(xe.z, ge.z, re.z, inv << 29, q, bc, acc);
                 o.w = bwd_elem<METHOD, CLAMP, NOISE, false, false>(xe.w, ge.w, re.w, inv << 28, q, bc, acc);
                 if (gx) st_stream4(gx + p, o);
+            }
+            if (MBAR) {
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&s_emp[st]);
             }
         }
         if (++in_group == kFlatGroup) {
@@ -1574,15 +1603,16 @@ inline int flat_cap() {
     }
     return cap;
 }
-// Largest tensor (elements) the flat backward takes (2^28: with the interleaved partition it
-// matches or beats the dynamically scheduled streaming kernel + finalize launch up to there;
-// beyond, the streaming kernel stays).  MHAQ_FQ_FLAT_MAX_LOG2 overrides (0 disables the flat kernel).
+// Largest tensor (elements) the flat backward takes.  With the interleaved partition and the
+// mbarrier-released ring it beats the dynamically scheduled streaming kernel + finalize launch at
+// every size measured (2^30: 1877 vs 1981 us), so there is no upper limit in practice.
+// MHAQ_FQ_FLAT_MAX_LOG2 overrides (0 disables the flat kernel).
 inline int64_t flat_max_elems() {
     static int64_t mx = -1;
     if (mx < 0) {
         const char *e = getenv("MHAQ_FQ_FLAT_MAX_LOG2");
-        const int l2 = e ? atoi(e) : 28;
-        mx = l2 <= 0 ? 0 : (int64_t)1 << l2;
+        const int l2 = e ? atoi(e) : 40;
+        mx = l2 <= 0 ? 0 : (int64_t)1 << (l2 > 62 ? 62 : l2);
     }
     return mx;
 }
@@ -1592,6 +1622,17 @@ inline int64_t flat_interleave_min() {
     if (mn < 0) {
         const char *e = getenv("MHAQ_FQ_FLAT_INTERLEAVE_LOG2");
         const int l2 = e ? atoi(e) : 24;
+        mn = (int64_t)1 << (l2 < 0 ? 0 : (l2 > 62 ? 62 : l2));
+    }
+    return mn;
+}
+// Tensors of at least this many elements release the staging ring through mbarriers instead of a
+// block barrier per batch (see the kernel).
+inline int64_t flat_mbar_min() {
+    static int64_t mn = -1;
+    if (mn < 0) {
+        const char *e = getenv("MHAQ_FQ_FLAT_MBAR_LOG2");
+        const int l2 = e ? atoi(e) : 26;
         mn = (int64_t)1 << (l2 < 0 ? 0 : (l2 > 62 ? 62 : l2));
     }
     return mn;
@@ -1610,21 +1651,27 @@ int launch_bwd_flat(bool explicit_r, const FlatGeom &f, cudaStream_t st, const f
                     float *gx, const QParams &prm, const float *r, uint64_t seed, uint64_t offset,
                     const uint64_t *philox_dev, double *ws, unsigned int *ticket, float *o0, float *o1,
                     float *o2, float *o3) {
-#define MHAQ_FLAT(N)                                                                              \
+#define MHAQ_FLAT2(N, M)                                                                          \
     do {                                                                                          \
         static bool attr_set = false;                                                             \
         if (!attr_set) {                                                                          \
-            cudaFuncSetAttribute(fq_bwd_flat_kernel<METHOD, CLAMP, N>,                            \
+            cudaFuncSetAttribute(fq_bwd_flat_kernel<METHOD, CLAMP, N, M>,                         \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kFlatSmemBytes);    \
             attr_set = true;                                                                      \
         }                                                                                         \
-        fq_bwd_flat_kernel<METHOD, CLAMP, N><<<f.grid, kFlatThreads, kFlatSmemBytes, st>>>(       \
+        fq_bwd_flat_kernel<METHOD, CLAMP, N, M><<<f.grid, kFlatThreads, kFlatSmemBytes, st>>>(    \
             go, x, gx, prm, f, r, seed, offset, philox_dev, ws, ticket, o0, o1, o2, o3,           \
             flat_exp_flags());                                                                    \
+    } while (0)
+#define MHAQ_FLAT(N)                                                                              \
+    do {                                                                                          \
+        if (f.n >= flat_mbar_min()) MHAQ_FLAT2(N, true);                                          \
+        else MHAQ_FLAT2(N, false);                                                                \
     } while (0)
     if (METHOD == MHAQ_FQ_LSQ) MHAQ_FLAT(NOISE_NONE);
     else if (explicit_r) MHAQ_FLAT(NOISE_EXPLICIT);
     else MHAQ_FLAT(NOISE_PHILOX);
+#undef MHAQ_FLAT2
 #undef MHAQ_FLAT
     return last_error();
 }

@@ -425,7 +425,7 @@ def test_graph_capture_gets_its_own_scratch_arena(fq):
 # full-size checks (BASELINE config 2): the oracle's ATen chain runs on the GPU
 # itself as the checker; plus size-independent properties
 # ---------------------------------------------------------------------------
-@pytest.mark.parametrize("log2n,bits", [(26, 4), (28, 8), (30, 4)])     # flat kernel (<= 2^28) and streaming (2^30)
+@pytest.mark.parametrize("log2n,bits", [(26, 4), (28, 8), (30, 4)])     # the single-launch flat kernel at every size
 def test_full_size_vs_oracle_on_device(fq, log2n, bits):
     n = 1 << log2n
     g = torch.Generator(device="cuda").manual_seed(0)
