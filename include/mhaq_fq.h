@@ -178,8 +178,8 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets,
  * whose block 0 sums the per-block fp64 records in index order (handed over through
  * self-validating words in `tickets`: no fence, no atomic) and writes the gradients — no second
  * launch, no per-task flushes; bitwise reproducible on a given device.
- * Everything else runs the two launches above.  mhaq_fq_bwd_single_launch() tells which (for
- * 16-byte aligned operands). */
+ * Everything else runs the two launches above (also an unclamped per-tensor tensor of 2^26 elements
+ * or more).  mhaq_fq_bwd_single_launch() tells which (for 16-byte aligned, clamped operands). */
 int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx,
                           const float *scale, const float *zp, const float *lo, const float *hi,
                           int scale_stride, int zp_stride, int lo_stride, int hi_stride, int param_mode,

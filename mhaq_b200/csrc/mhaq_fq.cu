@@ -1887,7 +1887,10 @@ int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx, const floa
     if (!go || !ws || !tickets) return MHAQ_FQ_ENULL;
     if (n_rows == 0 || n_inner == 0) return 0;
     const bool aligned = aligned16(x) && aligned16(go) && (!gx || aligned16(gx)) && (!r || aligned16(r));
-    if (aligned && flat_shape_ok(n_rows, n_inner, n_ch, method, go_is_code_grad)) {
+    // (an UNCLAMPED per-tensor tensor of 2^26 elements or more — never an activation — is the one
+    // case the streaming kernel still wins: 466 vs 498 us at 2^28, tools/exp_flat_unclamped2.py)
+    const bool flat_wins = has_clamp(param_mode, lo, hi) || n_inner < flat_mbar_min();
+    if (aligned && flat_wins && flat_shape_ok(n_rows, n_inner, n_ch, method, go_is_code_grad)) {
         if (!stride_ok(scale_stride) || !stride_ok(zp_stride) || !stride_ok(lo_stride) ||
             !stride_ok(hi_stride))
             return MHAQ_FQ_EINVAL;
