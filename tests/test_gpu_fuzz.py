@@ -183,3 +183,22 @@ def test_fuzz_against_the_live_reference(fq, ref, seed):
         C.assert_param_grad(l_o.grad, l_r.grad, ex[2], REL, "g_lo " + tag, floor)
     if use_hi:
         C.assert_param_grad(h_o.grad, h_r.grad, ex[3], REL, "g_hi " + tag, floor)
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_fuzz_per_channel_weights_all_estimators(fq, ref, seed):
+    """Weight-style tensors (per-channel, no clamp, calibration-formula scale) at random [C, inner]
+    shapes and bit widths, every estimator the reference can run — AEWGS included, whose input
+    gradient depends on per-channel fp32 means (1e-5 relative instead of bit-exact)."""
+    from tests.test_gpu_live_reference import _check_per_channel, _per_channel_case
+    rng = random.Random(7000 + seed)
+    C_ = rng.choice([1, 2, 3, 16, 48, 64, 130, 512])
+    inner = rng.choice([1, 2, 9, 27, 144, 576, 1152, 4095, 4096, 4608, 8192 + 5, 20000])
+    if C_ * inner < 2:
+        inner = 9
+    bits = rng.choice([1, 2, 3, 4, 8])
+    method = rng.choice(["STE", "LSQ", "AEWGS", "AEWGS"])
+    x, go, scale, zp = _per_channel_case(C_, inner, bits, seed=seed)
+    if inner == 1:                                   # max == min: the calibration formula gives scale 0
+        scale = torch.full_like(scale, 0.125)
+    _check_per_channel(fq, ref, x, go, scale, zp, method, bits, philox=(17, seed))
