@@ -107,11 +107,25 @@ __device__ __forceinline__ float absmax4(float m, const float4 &v) {
 // 16-byte record {cmin, cmax, xmin, xmax} per task (min / max are exact and order-free).  A
 // persistent variant (one record per CTA, 148 x 8 CTAs) was measured at 0.82-0.86 of the copy
 // peak against 1.03 for the plain forward (profiles/r02_exp_eval_persistent.txt) and dropped.
+// ---- programmatic dependent launch (PDL) of the eval-statistics finalize kernel ----
+// fq_minmax_finalize_kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it
+// may become resident while the forward kernel's last CTAs are still running, and calls pdl_wait()
+// (griddepcontrol.wait: the prerequisite grid has completed and its memory is visible) before
+// it touches a record — its launch latency overlaps the producer's tail instead of following it
+// (-0.4 ... -0.7 us per eval forward at every size).  The STATS forward calls pdl_trigger() on
+// entry; after a kernel that never triggers (anything else in the stream) the launch degrades to
+// ordinary stream order.  Works under stream capture.  Measured and NOT kept for the backward's
+// finalize and the AEWGS statistics finalize: +1 ... +3 us with 64-512 channels
+// (profiles/r02_exp_pdl.txt).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <bool VEC, bool CLAMP, bool STATS>
 __global__ void __launch_bounds__(kThreads)
 fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restrict__ codes,
               QParams prm, Geom g, double *__restrict__ mm_ws) {
     const int tid = threadIdx.x;
+    if (STATS) pdl_trigger();                        // the statistics finalize may start launching
     __shared__ float s_red[4][kThreads / 32];
     for (int64_t t = blockIdx.x; t < g.n_tasks; t += gridDim.x) {
         FwdStat st = {INFINITY, -INFINITY, INFINITY, -INFINITY};
@@ -220,12 +234,13 @@ fq_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, float *__restr
 // (one 128-bit load per record, every load of a thread independent of the others)
 constexpr int kMmThreads = 1024;
 __global__ void __launch_bounds__(kMmThreads)
-fq_minmax_finalize_kernel(const double *__restrict__ ws, int64_t n_rec, float *__restrict__ out5) {
+fq_minmax_finalize_kernel(const double *ws, int64_t n_rec, float *__restrict__ out5) {
     __shared__ float s[4][kMmThreads / 32];
+    pdl_wait();                                      // the forward kernel's records are complete and visible
     const float4 *rec = reinterpret_cast<const float4 *>(ws);
     float v[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
     for (int64_t t = threadIdx.x; t < n_rec; t += kMmThreads) {
-        const float4 r = __ldg(rec + t);
+        const float4 r = __ldcg(rec + t);
         v[0] = min_nan(v[0], r.x); v[1] = max_nan(v[1], r.y);
         v[2] = min_nan(v[2], r.z); v[3] = max_nan(v[3], r.w);
     }
@@ -544,7 +559,7 @@ __device__ __forceinline__ void finalize_channel(const double *ws, double *slice
     for (int64_t i = i0 + tid; i < i1; i += nthr) {
         const double *rec = ws + chan_record(g, ch, i) * kNPart;
 #pragma unroll
-        for (int m = 0; m < NCOL; ++m) a[m] += rec[m];
+        for (int m = 0; m < NCOL; ++m) a[m] += __ldcg(rec + m);
     }
     block_sum_cols<NCOL>(a, s);
     if (n_sl == 1) {
@@ -609,7 +624,7 @@ __device__ __forceinline__ void emit_param_grads(const QParams &prm, int64_t ch,
 }
 
 __global__ void __launch_bounds__(kFinThreads)
-fq_bwd_finalize_kernel(const double *__restrict__ ws, double *slice_ws, unsigned int *tickets,
+fq_bwd_finalize_kernel(const double *ws, double *slice_ws, unsigned int *tickets,
                        Geom g, int64_t n_sl, QParams prm, float *__restrict__ o0,
                        float *__restrict__ o1, float *__restrict__ o2, float *__restrict__ o3) {
     finalize_channel<5>(ws, slice_ws, tickets, g, n_sl, [=](int64_t ch, const double (&a)[5]) {
@@ -1353,8 +1368,9 @@ fq_aewgs_stats_kernel(const float *__restrict__ go, const float *__restrict__ x,
 }
 
 __global__ void __launch_bounds__(256)
-fq_aewgs_stats_finalize_kernel(const double *__restrict__ ws, Geom g, float *__restrict__ stats) {
+fq_aewgs_stats_finalize_kernel(const double *ws, Geom g, float *__restrict__ stats) {
     __shared__ double s[3][256];
+
     const int64_t ch = blockIdx.x;
     const int64_t rows_per_ch = g.n_rows / g.n_ch;
     const int64_t recs = rows_per_ch * g.tasks_per_row;
@@ -1364,7 +1380,7 @@ fq_aewgs_stats_finalize_kernel(const double *__restrict__ ws, Geom g, float *__r
         const int64_t j = i - rr * g.tasks_per_row;
         const int64_t t = (rr * g.n_ch + ch) * g.tasks_per_row + j;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) a[m] += ws[t * kNPart + m];
+        for (int m = 0; m < 3; ++m) a[m] += __ldcg(ws + t * kNPart + m);
     }
 #pragma unroll
     for (int m = 0; m < 3; ++m) s[m][threadIdx.x] = a[m];
@@ -1541,6 +1557,26 @@ inline Geom reduce_geom(int64_t n_rows, int64_t n_inner, int64_t n_ch) {
 inline int last_error() {
     cudaError_t e = cudaGetLastError();
     return (int)e;
+}
+
+// Launch a finalize kernel as a programmatic dependent of the kernel before it in the stream
+// (see pdl_wait / pdl_trigger).  MHAQ_FQ_NO_PDL=1 falls back to an ordinary launch.
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    static const int no_pdl = env_int("MHAQ_FQ_NO_PDL");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) return (int)e;
+    return last_error();
 }
 
 template <int METHOD, bool CLAMP, int NOISE>
@@ -1804,8 +1840,7 @@ int mhaq_fq_minmax_finalize(const double *minmax_ws, int64_t n_rows, int64_t n_i
     if (!minmax_ws || !out5) return MHAQ_FQ_ENULL;
     const int64_t n_tasks = mhaq_fq_num_tasks(n_rows, n_inner);
     if (n_tasks <= 0) return MHAQ_FQ_EINVAL;
-    fq_minmax_finalize_kernel<<<1, kMmThreads, 0, (cudaStream_t)stream>>>(minmax_ws, n_tasks, out5);
-    return last_error();
+    return launch_pdl(fq_minmax_finalize_kernel, 1, kMmThreads, (cudaStream_t)stream, minmax_ws, n_tasks, out5);
 }
 
 int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx, const float *scale,
