@@ -190,7 +190,7 @@ def _workspace(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
 # training path allocates nothing per call.  Bounded: the least recently used stream's entry is
 # dropped beyond _ARENA_MAX streams.
 _ARENA_MAX = 16
-_FLAT_REC_U32 = 4 + 2048 * 12          # include/mhaq_fq.h: mhaq_fq_ticket_count
+_ticket_need_cache = {}
 _arenas = {}
 
 
@@ -221,8 +221,13 @@ def _arena(x: torch.Tensor) -> _Arena:
 
 
 def _tickets(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
-    # == mhaq_fq_ticket_count: per-channel tickets + the flat backward's record region
-    need = (geo.n_ch if geo.n_ch > 0 else 1) + _FLAT_REC_U32
+    # per-channel tickets + the flat backward's record region (include/mhaq_fq.h)
+    n_ch = geo.n_ch if geo.n_ch > 0 else 1
+    need = _ticket_need_cache.get(n_ch)
+    if need is None:
+        if len(_ticket_need_cache) > 4096:
+            _ticket_need_cache.clear()
+        need = _ticket_need_cache[n_ch] = int(lib.mhaq_fq_ticket_count(geo.n_rows, geo.n_inner, n_ch))
     a = _arena(x)
     buf = a.tickets
     if buf is None or buf.numel() < need:

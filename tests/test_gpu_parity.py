@@ -354,7 +354,7 @@ def test_flat_backward_record_handover_is_stateless(fq):
     gx = torch.empty_like(x)
     out = torch.zeros(4, 1, device="cuda")
     ws = ops._workspace(x, L.geo)
-    tk2 = torch.zeros(1 + 4 + 2048 * 12, dtype=torch.int32, device="cuda")
+    tk2 = torch.zeros(ops.lib.mhaq_fq_ticket_count(1, n, 1), dtype=torch.int32, device="cuda")
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
 
