@@ -220,7 +220,7 @@ def _arena(x: torch.Tensor) -> _Arena:
     return a
 
 
-def _tickets(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
+def _tickets(x: torch.Tensor, geo: Geometry, a: Optional[_Arena] = None) -> torch.Tensor:
     # per-channel tickets + the flat backward's record region (include/mhaq_fq.h)
     n_ch = geo.n_ch if geo.n_ch > 0 else 1
     need = _ticket_need_cache.get(n_ch)
@@ -228,7 +228,8 @@ def _tickets(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
         if len(_ticket_need_cache) > 4096:
             _ticket_need_cache.clear()
         need = _ticket_need_cache[n_ch] = int(lib.mhaq_fq_ticket_count(geo.n_rows, geo.n_inner, n_ch))
-    a = _arena(x)
+    if a is None:
+        a = _arena(x)
     buf = a.tickets
     if buf is None or buf.numel() < need:
         n = max(32768, 1 << (int(need) - 1).bit_length())
@@ -236,11 +237,12 @@ def _tickets(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
     return buf
 
 
-def _shared_workspace(x: torch.Tensor, geo: Geometry) -> torch.Tensor:
+def _shared_workspace(x: torch.Tensor, geo: Geometry, a: Optional[_Arena] = None) -> torch.Tensor:
     """The stream's reusable record workspace (a CUDA-graph capture has an arena of its own, so a
     captured call never aliases scratch that eager calls keep using)."""
     need = _ws_bytes(geo) // 8
-    a = _arena(x)
+    if a is None:
+        a = _arena(x)
     buf = a.ws
     if buf is None or buf.numel() < need:
         n = max(1 << 15, 1 << (int(need) - 1).bit_length())
@@ -470,9 +472,10 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
             raise NotImplementedError("per-tensor AEWGS needs the linear parameter mode")
         return _backward_aewgs_dim0(go, x, L, code_grad, noise, need_gx, philox)
     stats = aewgs_stats(go, x, L, code_grad) if method == METHOD_IDS["AEWGS"] else None
-    ws = _shared_workspace(x, geo)
+    arena = _arena(x)
+    ws = _shared_workspace(x, geo, arena)
     noise, seed, offset, pdev = _noise_source(x, method, noise, philox)
-    tk = _tickets(x, geo)
+    tk = _tickets(x, geo, arena)
     # one C call: backward + deterministic reduction (ONE kernel for per-tensor STE / LSQ,
     # otherwise the streaming backward followed by the finalize kernel)
     check(lib.mhaq_fq_bwd_fused_f32(_ptr(go), _ptr(x), _ptr(gx), *L.params(),
