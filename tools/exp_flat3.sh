@@ -1,4 +1,7 @@
 #!/bin/bash
+# HISTORICAL (results: profiles/r02_exp_flat3.txt).  The variants were compile-time switches
+# (-DMHAQ_FLAT_SYNC=0|1 -DMHAQ_FLAT_POLL=0|1) of the work tree between commits 5fbdd13 and f20cc5e, built into
+# tools/_exp/ (git-ignored); the losing paths were removed from the source afterwards.
 # Flat backward v2: "empty"-mbarrier ring (S) and polled self-validating records (P) against the
 # block-barrier ring + fence/ticket epilogue (s0p0 = what r02_midsize.md's "final" row measured).
 echo "== correctness (default build = S1 P1)"

@@ -1,4 +1,6 @@
 #!/bin/bash
+# HISTORICAL (results: profiles/r02_exp_flat4.txt).  Variants = -DMHAQ_FLAT_SYNC / -DMHAQ_FLAT_POLL / -DMHAQ_FLAT_READER0
+# builds of the work tree just before commit f20cc5e (tools/_exp/, git-ignored); the losing paths were removed afterwards.
 # flat backward v2 diagnosis: which of {ring release (S), polled records (P), reader block (R)} costs what, at which size
 E=/root/repo/tools/_exp
 for lib in s0p0 s1p0 s0p1r0 s0p1r1 s1p1r0; do

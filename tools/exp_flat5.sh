@@ -1,4 +1,6 @@
 #!/bin/bash
+# HISTORICAL (results: profiles/r02_exp_flat5.txt).  sync1 = -DMHAQ_FLAT_SYNC=1 build of the work tree just before commit
+# b5afa74; both variants now live in the library as the MBAR template parameter (MHAQ_FQ_FLAT_MBAR_LOG2 switches at run time).
 # flat backward: block barrier per batch (default) vs the same refill point signalled through an
 # "empty" mbarrier (no block barrier, still ONE batch in flight during compute)
 E=/root/repo/tools/_exp
