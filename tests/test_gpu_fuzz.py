@@ -26,7 +26,8 @@ from oracle import ref_loader
 pytestmark = pytest.mark.gpu
 
 REL = 1e-5
-N_CASES = int(os.environ.get("MHAQ_FUZZ_CASES", "96"))     # more seeds: MHAQ_FUZZ_CASES=1000 pytest ...
+N_CASES = int(os.environ.get("MHAQ_FUZZ_CASES", "96"))
+N_LAYER_CASES = int(os.environ.get("MHAQ_FUZZ_LAYER_CASES", "24"))     # more seeds: MHAQ_FUZZ_CASES=1000 pytest ...
 
 
 @pytest.fixture(scope="module")
@@ -203,3 +204,149 @@ def test_fuzz_per_channel_weights_all_estimators(fq, ref, seed):
     if inner == 1:                                   # max == min: the calibration formula gives scale 0
         scale = torch.full_like(scale, 0.125)
     _check_per_channel(fq, ref, x, go, scale, zp, method, bits, philox=(17, seed))
+
+
+# ---------------------------------------------------------------------------
+# layer level: NoisyAct / NoisyConv2d of this repo against the live reference's layers
+# ---------------------------------------------------------------------------
+class _SameNoise:
+    """Make both sides use the same noise: the tensor of `noises` whose SHAPE matches the quantized
+    tensor (the reference draws in backward, in autograd's order; this repo's ops take it in
+    forward) — the reference through torch.randint_like, this repo through the explicit `noise`
+    argument of every op a layer may route to."""
+
+    _OPS = ("act_fake_quant", "weight_fake_quant_rows", "weight_fake_quant_log", "weight_fake_quant", "fake_quant")
+
+    def __init__(self, *noises):
+        self.by_shape = {tuple(n.shape): n for n in noises}
+
+    def __enter__(self):
+        from mhaq_b200 import ops
+        self.ops = ops
+        self._rl = torch.randint_like
+        self._real = {name: getattr(ops, name) for name in self._OPS}
+        pick = lambda t: self.by_shape[tuple(t.shape)]
+        torch.randint_like = lambda t, high, **kw: (pick(t).to(t.dtype) + 0.5)
+
+        def wrap(real):
+            def f(x, *a, **kw):
+                kw.pop("philox", None)
+                lsq = ops._method_id(kw.get("method", "STE")) == ops.METHOD_IDS["LSQ"]
+                kw["noise"] = None if lsq else pick(x)
+                return real(x, *a, **kw)
+            return f
+        for name, real in self._real.items():
+            setattr(ops, name, wrap(real))
+        return self
+
+    def __exit__(self, *a):
+        torch.randint_like = self._rl
+        for name, real in self._real.items():
+            setattr(self.ops, name, real)
+
+
+def _scalar_floor(n, gmax, vmax, smax):
+    return 2e-7 * math.sqrt(n) * gmax * (vmax + 4 + 0.5 * smax)
+
+
+@pytest.mark.parametrize("seed", range(N_LAYER_CASES))
+def test_fuzz_noisy_act_layer(fq, ref, seed):
+    """NoisyAct (log-domain parameters, signed / unsigned, training forward + backward, eval forward
+    and `bw`) at random shapes and parameter values, same noise on both sides."""
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_act import NoisyAct
+    rng = random.Random(9000 + seed)
+    g = torch.Generator(device="cuda").manual_seed(9000 + seed)
+    shape = rng.choice([(2, 16, 14, 14), (1, 3, 7, 9), (5, 33, 8, 8), (64, 50), (4096 * 3 + 17,), (2, 8, 31, 33)])
+    signed = rng.random() < 0.5
+    log_s = float(rng.choice([-6, -4, -3, -2, -1.5, 0]))
+    bits = rng.choice([1, 2, 3, 4, 8])
+    log_q = log_s + bits + rng.choice([0.0, 0.0, 0.25])            # q = 2^bits * s (sometimes off-grid)
+    b = -(2.0 ** (log_q - 1)) * rng.choice([1.0, 0.8]) if signed else 0.0
+    x = torch.randn(shape, device="cuda", generator=g) * (2.0 ** (log_q - 1.5))
+    if not signed:
+        x = x.abs()
+    if len(shape) == 4 and rng.random() < 0.5:
+        x = x.contiguous(memory_format=torch.channels_last)
+    go = torch.randn(shape, device="cuda", generator=g)
+    ours = NoisyAct(signed=signed).cuda()
+    theirs = ref.NoisyAct(signed=signed).cuda()
+    for m in (ours, theirs):
+        with torch.no_grad():
+            m.log_act_s.fill_(log_s); m.log_act_q.fill_(log_q); m.act_b.fill_(b)
+        m.train()
+    r = _kernel_noise(fq, x, torch.ones(1, device="cuda"), 21, seed)
+    xo = x.detach().clone().requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    with _SameNoise(r):
+        yr = theirs(xr); yr.backward(go)
+        yo = ours(xo); yo.backward(go)
+    tag = f"seed {seed}: {shape} signed={signed} log_s={log_s} log_q={log_q} b={b}"
+    C.assert_bit_exact(yo, yr, "y " + tag)
+    C.assert_bit_exact(xo.grad, xr.grad, "gx " + tag)
+    s = 2.0 ** log_s
+    floor = _scalar_floor(x.numel(), float(go.abs().max()), 2.0 ** (log_q - log_s), s) * s * math.log(2) * 4
+    for name in ("log_act_s", "log_act_q") + (("act_b",) if signed else ()):
+        a, e = getattr(ours, name).grad, getattr(theirs, name).grad
+        C.assert_close_rel(a, e, REL, f"g_{name} " + tag, abs_floor=floor)
+    # eval: y, bw
+    ours.eval(); theirs.eval()
+    with torch.no_grad():
+        ye_o, ye_r = ours(x), theirs(x)
+    C.assert_bit_exact(ye_o, ye_r, "y eval " + tag)
+    C.assert_bit_exact(ours.bw.reshape(-1), theirs.bw.reshape(-1), "bw " + tag)
+
+
+@pytest.mark.parametrize("seed", range(N_LAYER_CASES))
+def test_fuzz_noisy_conv2d_layer(fq, ref, seed):
+    """NoisyConv2d (per-channel / per-tensor, STE / LSQ, optional quantized bias): the quantized
+    weight the convolution sees, and the gradients of weight and log_wght_s, same noise on both
+    sides.  cuDNN runs the identical convolution on both sides (deterministic, TF32 off)."""
+    from mhaq_b200.aux.types import QScheme
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
+    rng = random.Random(12000 + seed)
+    torch.manual_seed(12000 + seed)
+    cin, cout = rng.choice([1, 3, 8, 16, 50]), rng.choice([1, 4, 16, 48, 130])
+    k = rng.choice([1, 3, 3, 5])
+    per_channel = rng.random() < 0.7
+    method = rng.choice(["STE", "LSQ"])
+    bias = rng.random() < 0.5
+    quant_bias = bias and per_channel and rng.random() < 0.5
+    log_s = float(rng.choice([-7, -5, -4, -3]))
+    kw = dict(padding=k // 2, bias=bias)
+    ours = NoisyConv2d(cin, cout, k, qscheme=QScheme.PER_CHANNEL if per_channel else QScheme.PER_TENSOR,
+                       qnmethod=QNMethod[method], quant_bias=quant_bias, **kw).cuda()
+    theirs = ref.NoisyConv2d(cin, cout, k, qscheme=ref.QScheme.PER_CHANNEL if per_channel else ref.QScheme.PER_TENSOR,
+                             qnmethod=ref.QNMethod[method], quant_bias=quant_bias, **kw).cuda()
+    with torch.no_grad():
+        theirs.weight.copy_(ours.weight)
+        if bias:
+            theirs.bias.copy_(ours.bias)
+        for m in (ours, theirs):
+            m.log_wght_s.fill_(log_s)
+    x = torch.randn(2, cin, 9, 9, device="cuda")
+    go = torch.randn(2, cout, 9, 9, device="cuda")
+    rw = (torch.randint(0, 2, tuple(ours.weight.shape), device="cuda").float() - 0.5)
+    rb = (torch.randint(0, 2, (cout,), device="cuda").float() - 0.5)
+    flags = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = False, True, False
+    try:
+        ours.train(); theirs.train()
+        with _SameNoise(rw, rb):
+            yr = theirs(x); yr.backward(go)
+        with _SameNoise(rw, rb):
+            yo = ours(x); yo.backward(go)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = flags
+    tag = f"seed {seed}: conv {cin}->{cout} k{k} {'pc' if per_channel else 'pt'} {method} bias={bias} qbias={quant_bias} log_s={log_s}"
+    C.assert_bit_exact(yo, yr, "conv output " + tag)                  # same quantized weight => same cuDNN result
+    C.assert_bit_exact(ours.weight.grad, theirs.weight.grad, "g_weight " + tag)
+    n_per = ours.weight[0].numel() if per_channel else ours.weight.numel()
+    gmax = float(theirs.weight.grad.abs().max()) + 1e-30
+    s = 2.0 ** log_s
+    wmax = float(ours.weight.detach().abs().max())
+    floor = _scalar_floor(n_per, gmax, 2 * wmax / s, s) * s * math.log(2) * 4
+    gs_r = theirs.log_wght_s.grad
+    C.assert_close_rel(ours.log_wght_s.grad, gs_r, REL, "g_log_wght_s " + tag, abs_floor=floor)
+    if bias:
+        C.assert_close_rel(ours.bias.grad, theirs.bias.grad, 1e-5, "g_bias " + tag, abs_floor=1e-6 * float(go.abs().sum(dim=(0, 2, 3)).max()))
