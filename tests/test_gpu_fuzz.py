@@ -296,9 +296,32 @@ def test_fuzz_noisy_act_layer(fq, ref, seed):
     C.assert_bit_exact(ours.bw.reshape(-1), theirs.bw.reshape(-1), "bw " + tag)
 
 
+def _exact_aewgs_weight_grad(w, log_s, G):
+    """d loss / d weight of the per-channel AEWGS weight path (gdnsq_conv2d.py:72-98 with
+    QNAEWGS.backward, gdnsq.py:113-147) in fp64, on the reference's own fp32-valued operands
+    (u, v, e and g = G*s are formed in fp32 exactly as the reference forms them; the per-channel
+    means, delta, gamma, the division by s and the amin scatter are fp64).  G = d loss / d weight_q."""
+    O_ = w.shape[0]
+    w2, G2 = w.detach().reshape(O_, -1), G.reshape(O_, -1)
+    s = torch.exp2(log_s.detach()).reshape(O_, 1)
+    zp = w2.amin(1, keepdim=True)
+    v = (w2 - zp) / s
+    e = torch.round(v) - v
+    g = G2 * s
+    e64, g64, s64 = e.double(), g.double(), s.double()
+    sg = torch.sign(g64)
+    num, e2, me = (sg * e64).mean(1, keepdim=True), (e64 * e64).mean(1, keepdim=True), e64.mean(1, keepdim=True)
+    delta = num / (e2 - me * me).clamp_min(1e-3)
+    gamma = (delta * (sg * e64)).clamp_max(1 - 0.01)
+    du = (g64 - g64 * gamma) / s64
+    dzp = G2.double().sum(1, keepdim=True) - du.sum(1, keepdim=True)
+    at_min = (w2 == zp)
+    return (du + at_min * (dzp / at_min.sum(1, keepdim=True))).reshape(w.shape)
+
+
 @pytest.mark.parametrize("seed", range(N_LAYER_CASES))
 def test_fuzz_noisy_conv2d_layer(fq, ref, seed):
-    """NoisyConv2d (per-channel / per-tensor, STE / LSQ, optional quantized bias): the quantized
+    """NoisyConv2d (per-channel / per-tensor, STE / LSQ / AEWGS, optional quantized bias): the quantized
     weight the convolution sees, and the gradients of weight and log_wght_s, same noise on both
     sides.  cuDNN runs the identical convolution on both sides (deterministic, TF32 off)."""
     from mhaq_b200.aux.types import QScheme
@@ -309,7 +332,7 @@ def test_fuzz_noisy_conv2d_layer(fq, ref, seed):
     cin, cout = rng.choice([1, 3, 8, 16, 50]), rng.choice([1, 4, 16, 48, 130])
     k = rng.choice([1, 3, 3, 5])
     per_channel = rng.random() < 0.7
-    method = rng.choice(["STE", "LSQ"])
+    method = rng.choice(["STE", "LSQ", "AEWGS"])
     bias = rng.random() < 0.5
     quant_bias = bias and per_channel and rng.random() < 0.5
     log_s = float(rng.choice([-7, -5, -4, -3]))
@@ -340,7 +363,29 @@ def test_fuzz_noisy_conv2d_layer(fq, ref, seed):
         torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = flags
     tag = f"seed {seed}: conv {cin}->{cout} k{k} {'pc' if per_channel else 'pt'} {method} bias={bias} qbias={quant_bias} log_s={log_s}"
     C.assert_bit_exact(yo, yr, "conv output " + tag)                  # same quantized weight => same cuDNN result
-    C.assert_bit_exact(ours.weight.grad, theirs.weight.grad, "g_weight " + tag)
+    if method == "AEWGS" and per_channel and not quant_bias:
+        # the input gradient depends on per-channel means which the reference takes in fp32
+        # (gdnsq.py:118-124) — over a few hundred elements they carry ~1e-4 relative noise, more
+        # than the 1e-5 bar; so: within 1e-5 of the reference, OR at least as close as the
+        # reference to the fp64 evaluation of its own formula
+        wq = ours.quantized_weight()[0].detach().requires_grad_(True)
+        G, = torch.autograd.grad(torch.nn.functional.conv2d(x, wq, None, padding=k // 2), wq, go)
+        ex = _exact_aewgs_weight_grad(ours.weight, ours.log_wght_s, G)
+        C.assert_param_grad(ours.weight.grad, theirs.weight.grad, ex, REL, "g_weight " + tag,
+                            4e-7 * float(theirs.weight.grad.abs().max()))
+    elif method == "AEWGS":
+        # per-tensor (statistics over dim 0 only: 1-130 elements per mean) or with the bias
+        # quantizer sharing the row minimum: no closed form at hand; where 1 - gamma is small the
+        # fp32 means of the reference show at a few 1e-5 relative
+        # (the row / tensor minimum also receives d/d zero_point = sum(G) - sum(du), a difference of
+        # two large sums the reference forms in fp32: checked by the exact rule above, skipped here)
+        wd = ours.weight.detach()
+        zp = wd.amin((1, 2, 3), keepdim=True) if per_channel else wd.amin()
+        keep = (wd != zp)
+        C.assert_close_rel(ours.weight.grad[keep], theirs.weight.grad[keep], 1e-4, "g_weight " + tag,
+                           abs_floor=1e-6 * float(theirs.weight.grad.abs().max()))
+    else:
+        C.assert_bit_exact(ours.weight.grad, theirs.weight.grad, "g_weight " + tag)
     n_per = ours.weight[0].numel() if per_channel else ours.weight.numel()
     gmax = float(theirs.weight.grad.abs().max()) + 1e-30
     s = 2.0 ** log_s
@@ -350,3 +395,52 @@ def test_fuzz_noisy_conv2d_layer(fq, ref, seed):
     C.assert_close_rel(ours.log_wght_s.grad, gs_r, REL, "g_log_wght_s " + tag, abs_floor=floor)
     if bias:
         C.assert_close_rel(ours.bias.grad, theirs.bias.grad, 1e-5, "g_bias " + tag, abs_floor=1e-6 * float(go.abs().sum(dim=(0, 2, 3)).max()))
+
+
+@pytest.mark.parametrize("seed", range(N_LAYER_CASES))
+def test_fuzz_noisy_linear_layer(fq, ref, seed):
+    """NoisyLinear (per-tensor, STE / LSQ) against the live
+    reference's layer: output of F.linear on the quantized weight, weight / log_wght_s gradients."""
+    from mhaq_b200.aux.types import QScheme
+    from mhaq_b200.quantization.gdnsq.gdnsq_utils import QNMethod
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_linear import NoisyLinear
+    rng = random.Random(15000 + seed)
+    torch.manual_seed(15000 + seed)
+    fin, fout = rng.choice([1, 7, 64, 300, 1000]), rng.choice([1, 10, 100, 257])
+    # (the reference's per-channel NoisyLinear cannot run: gdnsq_linear.py:71 takes amin((1, 2, 3))
+    # of a 2-D weight — IndexError; per-tensor is the only form there is to compare with)
+    per_channel = False
+    method = rng.choice(["STE", "LSQ"])
+    bias = rng.random() < 0.6
+    log_s = float(rng.choice([-7, -5, -4, -3]))
+    mk = lambda cls, qs, qn: cls(fin, fout, bias=bias, qscheme=qs.PER_CHANNEL if per_channel else qs.PER_TENSOR,
+                                 qnmethod=qn[method]).cuda()
+    ours, theirs = mk(NoisyLinear, QScheme, QNMethod), mk(ref.NoisyLinear, ref.QScheme, ref.QNMethod)
+    with torch.no_grad():
+        theirs.weight.copy_(ours.weight)
+        if bias:
+            theirs.bias.copy_(ours.bias)
+        for m in (ours, theirs):
+            m.log_wght_s.fill_(log_s)
+    x = torch.randn(5, fin, device="cuda")
+    go = torch.randn(5, fout, device="cuda")
+    rw = (torch.randint(0, 2, tuple(ours.weight.shape), device="cuda").float() - 0.5)
+    rb = (torch.randint(0, 2, (fout,), device="cuda").float() - 0.5)
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ours.train(); theirs.train()
+        with _SameNoise(rw, rb):
+            yr = theirs(x); yr.backward(go)
+        with _SameNoise(rw, rb):
+            yo = ours(x); yo.backward(go)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    tag = f"seed {seed}: linear {fin}->{fout} {'pc' if per_channel else 'pt'} {method} bias={bias} log_s={log_s}"
+    C.assert_bit_exact(yo, yr, "output " + tag)
+    C.assert_bit_exact(ours.weight.grad, theirs.weight.grad, "g_weight " + tag)
+    n_per = fin if per_channel else fin * fout
+    s = 2.0 ** log_s
+    floor = _scalar_floor(n_per, float(theirs.weight.grad.abs().max()) + 1e-30,
+                          2 * float(ours.weight.detach().abs().max()) / s, s) * s * math.log(2) * 4
+    C.assert_close_rel(ours.log_wght_s.grad, theirs.log_wght_s.grad, REL, "g_log_wght_s " + tag, abs_floor=floor)
