@@ -37,3 +37,31 @@ for name, big, parts in (("g_scale", gs, sums[0]), ("g_zp+g_lo", gb, sums[1]), (
     print(f"{name}: whole {float(big):.9g}  sum of slices {parts:.9g}  rel {rel:.2e}")
     ok &= rel < 1e-5
 print("INT64 INDEXING", "OK" if ok else "FAILED", f"(n = {n}, single_launch = {fq.ops.lib.mhaq_fq_bwd_single_launch(1, n, 1, 3, 0)})")
+
+# ---- per-channel [4100, 2^19] (2.15e9 elements) through the streaming kernels, LSQ
+del x, go, y, gx
+torch.cuda.empty_cache()
+R, I = 4100, 1 << 19
+x = torch.empty(R, I, device="cuda").normal_(generator=g)
+go = torch.empty(R, I, device="cuda").normal_(generator=g)
+sc = torch.full((R, 1), 0.25, device="cuda") * (1 + torch.arange(R, device="cuda").view(R, 1) % 3)
+zp = torch.full((R, 1), -2.0, device="cuda")
+
+
+def run_pc(xx, gg, s0, z0):
+    xs = xx.clone().requires_grad_(True)
+    s_, z_ = s0.clone().requires_grad_(True), z0.clone().requires_grad_(True)
+    y = fq.fake_quant(xs, s_, z_, -math.inf, math.inf, method="LSQ")
+    y.backward(gg)
+    return y.detach(), xs.grad, s_.grad, z_.grad
+
+
+y, gx, gs, gz = run_pc(x, go, sc, zp)
+ok2 = True
+for r0 in range(0, R, 1024):
+    r1 = min(r0 + 1024, R)
+    ys, gxs, a, c = run_pc(x[r0:r1], go[r0:r1], sc[r0:r1], zp[r0:r1])
+    e = [torch.equal(ys, y[r0:r1]), torch.equal(gxs, gx[r0:r1]), torch.equal(a, gs[r0:r1]), torch.equal(c, gz[r0:r1])]
+    ok2 &= all(e)
+    print(f"rows [{r0}, {r1}): y, gx, g_scale, g_zp equal: {e}", flush=True)
+print("INT64 INDEXING per-channel", "OK" if ok2 else "FAILED", f"({R} x {I} = {R * I} elements)")
