@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define MHAQ_FQ_ABI_VERSION 6
+#define MHAQ_FQ_ABI_VERSION 7
 
 /* gradient estimators — numeric values follow the reference enum
  * QNMethod (src/quantization/gdnsq/gdnsq_utils.py:9-13). */
@@ -190,6 +190,23 @@ int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx,
                           float *g_scale, float *g_zp, float *g_lo, float *g_hi, void *stream);
 int mhaq_fq_bwd_single_launch(int64_t n_rows, int64_t n_inner, int64_t n_ch, int method,
                               int go_is_code_grad);
+/* mhaq_fq_bwd_fused_f32 that also ADDS acc_scale / acc_zp / acc_lo / acc_hi (one value per channel,
+ * each may be NULL) to the gradient it writes for the corresponding parameter (in the log-domain
+ * modes: to the gradient of log_act_s / act_b / log_act_q, resp. log_wght_s / zero_point).  They are
+ * the gradients the same parameters receive along other paths of the caller's graph (PotentialLoss
+ * reads log_act_s and log_act_q, gdnsq_loss.py:114-168): with them folded in here autograd sees ONE
+ * gradient per parameter and the accumulation kernels it would otherwise launch (2 per activation
+ * quantizer per step) disappear.  The sum is the fp32 sum autograd would have formed. */
+int mhaq_fq_bwd_fused_acc_f32(const float *go, const float *x, float *gx,
+                              const float *scale, const float *zp, const float *lo, const float *hi,
+                              int scale_stride, int zp_stride, int lo_stride, int hi_stride, int param_mode,
+                              int64_t n_rows, int64_t n_inner, int64_t n_ch,
+                              int method, int go_is_code_grad,
+                              const float *r, uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                              const float *aewgs_stats, double *ws, unsigned int *tickets,
+                              float *g_scale, float *g_zp, float *g_lo, float *g_hi,
+                              const float *acc_scale, const float *acc_zp, const float *acc_lo,
+                              const float *acc_hi, void *stream);
 
 /* AEWGS statistics: per-channel sums of sign(g)*e, e*e, e  (e = rint(v)-v). */
 int mhaq_fq_aewgs_stats_f32(const float *go, const float *x,
@@ -260,6 +277,10 @@ typedef struct {
     const float *g_log_range, *g_row_min, *g_row_max, *r;   /* any may be NULL */
     float *g_w, *g_log_scale;                               /* either may be NULL */
     int64_t n_rows, n_inner;
+    /* optional (NULL = none): the gradient log_scale[row] receives along OTHER paths of the caller's
+     * graph (PotentialLoss reads log_wght_s directly); added to g_log_scale in the kernel so that
+     * autograd sees one gradient per parameter and launches no accumulation kernel */
+    const float *g_log_scale_acc;
 } mhaq_fq_wrow_bwd_desc;
 int mhaq_fq_wrow_multi_fwd_f32(const mhaq_fq_wrow_fwd_desc *descs, int n_tensors, void *stream);
 /* AEWGS (the one estimator with an exchange step) in the multi-tensor form: first

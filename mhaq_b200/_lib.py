@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # MHAQ_FQ_LIB: experiment knob to load an alternative build of the same ABI
 LIB_PATH = os.environ.get("MHAQ_FQ_LIB") or os.path.join(_HERE, "csrc", "libmhaq_fq.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 NPART = 8  # MHAQ_FQ_NPART
 
 class WRowFwdDesc(ctypes.Structure):
@@ -27,7 +27,7 @@ class WRowBwdDesc(ctypes.Structure):
     """mhaq_fq_wrow_bwd_desc"""
     _fields_ = [(n, c_void_p) for n in ("g_wq", "w", "log_scale", "row_min", "row_max", "g_log_range",
                                         "g_row_min", "g_row_max", "r", "g_w", "g_log_scale")] + [
-        ("n_rows", c_int64), ("n_inner", c_int64)]
+        ("n_rows", c_int64), ("n_inner", c_int64), ("g_log_scale_acc", c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/mhaq_fq.h one to one
@@ -50,6 +50,9 @@ _SIGNATURES = {
     "mhaq_fq_bwd_fused_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                       c_int64, c_int64, c_int64, c_int, c_int, _P, c_uint64, c_uint64,
                                       _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mhaq_fq_bwd_fused_acc_f32": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                          c_int64, c_int64, c_int64, c_int, c_int, _P, c_uint64, c_uint64,
+                                          _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mhaq_fq_bwd_single_launch": (c_int, [c_int64, c_int64, c_int64, c_int, c_int]),
     "mhaq_fq_aewgs_stats_f32": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                         c_int64, c_int64, c_int64, c_int, _P, _P]),

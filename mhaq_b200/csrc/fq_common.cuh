@@ -94,6 +94,11 @@ struct QParams {
     const float *scale, *zp, *lo, *hi;
     int ss, zs, ls, hs;
     int mode;
+    // optional: gradients that reach the same four parameters along OTHER paths of the caller's
+    // graph (one value per channel, NULL = none).  The reduction's last thread adds them to the
+    // gradients it emits, so autograd sees ONE gradient per parameter and launches no
+    // accumulation kernel (mhaq_fq_bwd_fused_acc_f32).
+    const float *acc0, *acc1, *acc2, *acc3;
 };
 
 // Per-channel constants held in registers for the lifetime of a task.

@@ -150,6 +150,8 @@ struct WRowBwdRow {
     float *gw, *g_log_s;         // this row's outputs (either may be NULL)
     float log_s, mn, mx;         // log_wght_s[row], row minimum / maximum from the forward
     float g_lr, g_mn, g_mx;      // gradients w.r.t. log_range / row_min / row_max of this row
+    float g_ls_acc;              // gradient log_wght_s[row] receives along the caller's other paths
+    bool has_acc;
     float delta;                 // AEWGS: this channel's delta from the (all-reduced) statistics
     bool has_glr, has_gmn, has_gmx;
     int64_t noise_row;           // row index inside ITS tensor: the noise stream's coordinate
@@ -247,7 +249,11 @@ __device__ __forceinline__ void wrow_bwd_row(const WRowBwdRow &d, int64_t n_inne
             gt = f_div(d.g_lr, f_mul(tt, kLn2f));
             g2 = f_mul(f_mul(gt, q.s), kLn2f);
         }
-        if (d.g_log_s) *d.g_log_s = d.has_glr ? f_add(g1, g2) : g1;
+        if (d.g_log_s) {
+            float gls = d.has_glr ? f_add(g1, g2) : g1;
+            if (d.has_acc) gls = f_add(gls, d.g_ls_acc);    // == autograd's AccumulateGrad of the two
+            *d.g_log_s = gls;
+        }
         // amin / amax backward: what flows into the row minimum and maximum
         float gmin = dzp;                                    // zero point = row minimum
         if (d.has_glr) gmin = f_add(gmin, -gt);            // SubBackward of (mx - mn)
@@ -309,6 +315,7 @@ fq_wrow_bwd_kernel(const float *__restrict__ go, const float *__restrict__ w, WR
         d.g_mx = d.has_gmx ? __ldg(g_row_max + row) : 0.f;
         d.noise_row = row;
         d.delta = 0.f;
+        d.has_acc = false; d.g_ls_acc = 0.f;
         wrow_bwd_row<METHOD, NOISE, VEC>(d, a.n_inner, key, s_red, s_d);
     }
 }
@@ -318,8 +325,9 @@ struct WRowBwdDesc {
     const float *g_wq, *w, *log_s, *row_min, *row_max, *g_log_range, *g_row_min, *g_row_max, *r;
     float *g_w, *g_log_s;
     int64_t n_inner;
+    const float *g_log_s_acc;
 };
-constexpr int kWRowMultiBwdMax = 24;      // 24 x 96 B of descriptors + tables < 4 KB of parameters
+constexpr int kWRowMultiBwdMax = 24;      // 24 x 104 B of descriptors + tables < 4 KB of parameters
 struct WRowBwdMulti {
     WRowBwdDesc d[kWRowMultiBwdMax];
     int row0[kWRowMultiBwdMax + 1];
@@ -360,6 +368,8 @@ fq_wrow_multi_bwd_kernel(const __grid_constant__ WRowBwdMulti m, uint64_t seed, 
         d.g_mx = d.has_gmx ? __ldg(e.g_row_max + r) : 0.f;
         d.noise_row = r;
         d.delta = 0.f;
+        d.has_acc = e.g_log_s_acc != nullptr;
+        d.g_ls_acc = d.has_acc ? __ldg(e.g_log_s_acc + r) : 0.f;
         if (METHOD == MHAQ_FQ_AEWGS) {
             const int64_t sr = stats_row0 + row;
             const float num = __ldg(stats + sr), e2 = __ldg(stats + stats_ld + sr), me = __ldg(stats + 2 * stats_ld + sr);

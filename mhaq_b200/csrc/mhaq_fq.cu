@@ -604,22 +604,31 @@ __device__ __forceinline__ void emit_param_grads(const QParams &prm, int64_t ch,
                                                  float *o0, float *o1, float *o2, float *o3) {
     const double ds = a[0] + a[1];
     constexpr double kLn2 = 0.693147180559945309417;
+    // (+ prm.accK: the gradient the same parameter receives along the caller's other paths, added in
+    // fp32 exactly as autograd's AccumulateGrad would add the two contributions)
+    const bool log1 = (prm.mode == PARAMS_ACT_LOG);
+    auto put = [&](float *o, const float *acc, double v) {
+        if (!o) return;
+        const int64_t i = log1 ? 0 : ch;
+        const float f = (float)v;
+        o[i] = acc ? __fadd_rn(f, acc[i]) : f;
+    };
     if (prm.mode == PARAMS_ACT_LOG) {
         const double s = (double)exp2f(prm.scale[0]), q = (double)exp2f(prm.lo[0]);
-        if (o0) o0[0] = (float)((ds - a[4]) * s * kLn2);
-        if (o1) o1[0] = (float)(a[2] + a[3] + a[4]);
-        if (o2) o2[0] = (float)(a[4] * q * kLn2);
+        put(o0, prm.acc0, (ds - a[4]) * s * kLn2);
+        put(o1, prm.acc1, a[2] + a[3] + a[4]);
+        put(o2, prm.acc2, a[4] * q * kLn2);
     } else if (prm.mode == PARAMS_WEIGHT_LOG) {
         const double s = (double)exp2f(prm.scale[ch * prm.ss]);
-        if (o0) o0[ch] = (float)(ds * s * kLn2);
-        if (o1) o1[ch] = (float)a[2];
+        put(o0, prm.acc0, ds * s * kLn2);
+        put(o1, prm.acc1, a[2]);
     } else if (prm.mode == PARAMS_UNIT) {
-        if (o0) o0[ch] = (float)a[1];
+        put(o0, prm.acc0, a[1]);
     } else {
-        if (o0) o0[ch] = (float)ds;
-        if (o1) o1[ch] = (float)a[2];
-        if (o2) o2[ch] = (float)a[3];
-        if (o3) o3[ch] = (float)a[4];
+        put(o0, prm.acc0, ds);
+        put(o1, prm.acc1, a[2]);
+        put(o2, prm.acc2, a[3]);
+        put(o3, prm.acc3, a[4]);
     }
 }
 
@@ -1725,7 +1734,7 @@ int wrow_multi_bwd_chunks(const mhaq_fq_wrow_bwd_desc *descs, int n_tensors, Lau
             const mhaq_fq_wrow_bwd_desc &d = descs[i];
             const int k = m.n++;
             m.d[k] = {d.g_wq, d.w, d.log_scale, d.row_min, d.row_max, d.g_log_range, d.g_row_min,
-                      d.g_row_max, d.r, d.g_w, d.g_log_scale, d.n_inner};
+                      d.g_row_max, d.r, d.g_w, d.g_log_scale, d.n_inner, d.g_log_scale_acc};
             m.vec[k] = (d.n_inner % 4 == 0) && aligned16(d.w) && aligned16(d.g_wq) &&
                        (!d.g_w || aligned16(d.g_w)) && (!d.r || aligned16(d.r));
             m.row0[k + 1] = m.row0[k] + (int)d.n_rows;
@@ -1881,17 +1890,19 @@ int mhaq_fq_bwd_f32(const float *go, const float *x, float *gx, const float *sca
 #undef MHAQ_BWD
 }
 
-int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets, const float *scale, const float *zp,
+static int bwd_finalize_impl(double *ws, unsigned int *tickets, const float *scale, const float *zp,
                              const float *lo, const float *hi, int scale_stride, int zp_stride,
                              int lo_stride, int hi_stride, int param_mode, int64_t n_rows,
                              int64_t n_inner, int64_t n_ch, float *g_scale, float *g_zp, float *g_lo,
-                             float *g_hi, void *stream) {
+                             float *g_hi, const float *const acc[4], void *stream) {
     if (!ws || !tickets) return MHAQ_FQ_ENULL;
     if (n_rows <= 0 || n_inner <= 0 || n_ch < 1 || (n_rows % n_ch) != 0) return MHAQ_FQ_EINVAL;
     int rc = check_mode(param_mode, lo, n_ch);
     if (rc) return rc;
     if (param_mode != PARAMS_LINEAR && !scale) return MHAQ_FQ_ENULL;
-    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode};
+    const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode,
+                         acc ? acc[0] : nullptr, acc ? acc[1] : nullptr, acc ? acc[2] : nullptr,
+                         acc ? acc[3] : nullptr};
     const Geom g = reduce_geom(n_rows, n_inner, n_ch);
     const int64_t n_sl = n_slices_of(g);
     if (n_sl * n_ch > 0x7fffffffLL) return MHAQ_FQ_EINVAL;
@@ -1904,18 +1915,27 @@ int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets, const float *sca
     return last_error();
 }
 
+int mhaq_fq_bwd_finalize_f32(double *ws, unsigned int *tickets, const float *scale, const float *zp,
+                             const float *lo, const float *hi, int scale_stride, int zp_stride,
+                             int lo_stride, int hi_stride, int param_mode, int64_t n_rows,
+                             int64_t n_inner, int64_t n_ch, float *g_scale, float *g_zp, float *g_lo,
+                             float *g_hi, void *stream) {
+    return bwd_finalize_impl(ws, tickets, scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride,
+                             param_mode, n_rows, n_inner, n_ch, g_scale, g_zp, g_lo, g_hi, nullptr, stream);
+}
+
 int mhaq_fq_bwd_single_launch(int64_t n_rows, int64_t n_inner, int64_t n_ch, int method,
                                  int go_is_code_grad) {
     return flat_shape_ok(n_rows, n_inner, n_ch, method, go_is_code_grad) ? 1 : 0;
 }
 
-int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx, const float *scale,
+static int bwd_fused_impl(const float *go, const float *x, float *gx, const float *scale,
                           const float *zp, const float *lo, const float *hi, int scale_stride,
                           int zp_stride, int lo_stride, int hi_stride, int param_mode, int64_t n_rows,
                           int64_t n_inner, int64_t n_ch, int method, int go_is_code_grad, const float *r,
                           uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
                           const float *aewgs_stats, double *ws, unsigned int *tickets, float *g_scale,
-                          float *g_zp, float *g_lo, float *g_hi, void *stream) {
+                          float *g_zp, float *g_lo, float *g_hi, const float *const acc[4], void *stream) {
     int rc = check_common(x, scale, zp, n_rows, n_inner, n_ch);
     if (rc) return rc;
     if ((rc = check_mode(param_mode, lo, n_ch)) != 0) return rc;
@@ -1929,7 +1949,9 @@ int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx, const floa
         if (!stride_ok(scale_stride) || !stride_ok(zp_stride) || !stride_ok(lo_stride) ||
             !stride_ok(hi_stride))
             return MHAQ_FQ_EINVAL;
-        const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode};
+        const QParams prm = {scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride, param_mode,
+                             acc ? acc[0] : nullptr, acc ? acc[1] : nullptr, acc ? acc[2] : nullptr,
+                             acc ? acc[3] : nullptr};
         const FlatGeom f = make_flat_geom(n_inner, flat_cap(), n_inner >= flat_interleave_min());
         const bool clamp = has_clamp(param_mode, lo, hi);
         cudaStream_t st = (cudaStream_t)stream;
@@ -1948,9 +1970,34 @@ int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx, const floa
                          param_mode, n_rows, n_inner, n_ch, method, go_is_code_grad, r, seed, offset,
                          philox_dev, aewgs_stats, ws, stream);
     if (rc) return rc;
-    return mhaq_fq_bwd_finalize_f32(ws, tickets, scale, zp, lo, hi, scale_stride, zp_stride, lo_stride,
-                                    hi_stride, param_mode, n_rows, n_inner, n_ch, g_scale, g_zp, g_lo,
-                                    g_hi, stream);
+    return bwd_finalize_impl(ws, tickets, scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride,
+                             param_mode, n_rows, n_inner, n_ch, g_scale, g_zp, g_lo, g_hi, acc, stream);
+}
+
+int mhaq_fq_bwd_fused_f32(const float *go, const float *x, float *gx, const float *scale,
+                          const float *zp, const float *lo, const float *hi, int scale_stride,
+                          int zp_stride, int lo_stride, int hi_stride, int param_mode, int64_t n_rows,
+                          int64_t n_inner, int64_t n_ch, int method, int go_is_code_grad, const float *r,
+                          uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                          const float *aewgs_stats, double *ws, unsigned int *tickets, float *g_scale,
+                          float *g_zp, float *g_lo, float *g_hi, void *stream) {
+    return bwd_fused_impl(go, x, gx, scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride,
+                          param_mode, n_rows, n_inner, n_ch, method, go_is_code_grad, r, seed, offset,
+                          philox_dev, aewgs_stats, ws, tickets, g_scale, g_zp, g_lo, g_hi, nullptr, stream);
+}
+
+int mhaq_fq_bwd_fused_acc_f32(const float *go, const float *x, float *gx, const float *scale,
+                              const float *zp, const float *lo, const float *hi, int scale_stride,
+                              int zp_stride, int lo_stride, int hi_stride, int param_mode, int64_t n_rows,
+                              int64_t n_inner, int64_t n_ch, int method, int go_is_code_grad, const float *r,
+                              uint64_t seed, uint64_t offset, const uint64_t *philox_dev,
+                              const float *aewgs_stats, double *ws, unsigned int *tickets, float *g_scale,
+                              float *g_zp, float *g_lo, float *g_hi, const float *acc_scale,
+                              const float *acc_zp, const float *acc_lo, const float *acc_hi, void *stream) {
+    const float *const acc[4] = {acc_scale, acc_zp, acc_lo, acc_hi};
+    return bwd_fused_impl(go, x, gx, scale, zp, lo, hi, scale_stride, zp_stride, lo_stride, hi_stride,
+                          param_mode, n_rows, n_inner, n_ch, method, go_is_code_grad, r, seed, offset,
+                          philox_dev, aewgs_stats, ws, tickets, g_scale, g_zp, g_lo, g_hi, acc, stream);
 }
 
 int mhaq_fq_aewgs_stats_f32(const float *go, const float *x, const float *scale, const float *zp,

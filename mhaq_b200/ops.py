@@ -457,7 +457,7 @@ def _noise_source(x, method: int, noise, philox):
 
 
 def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_gx: bool,
-                   philox=None):
+                   philox=None, acc=None):
     geo = L.geo
     go = _like_layout(go, x)
     gx = torch.empty_like(x) if need_gx else None
@@ -478,11 +478,21 @@ def _backward_impl(go, x, L: _Launch, method: int, code_grad: bool, noise, need_
     tk = _tickets(x, geo, arena)
     # one C call: backward + deterministic reduction (ONE kernel for per-tensor STE / LSQ,
     # otherwise the streaming backward followed by the finalize kernel)
-    check(lib.mhaq_fq_bwd_fused_f32(_ptr(go), _ptr(x), _ptr(gx), *L.params(),
-                                    geo.n_rows, geo.n_inner, geo.n_ch, method, int(code_grad),
-                                    _ptr(noise), seed, offset, _ptr(pdev), _ptr(stats), _ptr(ws), _ptr(tk),
-                                    _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream()),
-          "mhaq_fq_bwd_fused_f32")
+    if acc is None:
+        check(lib.mhaq_fq_bwd_fused_f32(_ptr(go), _ptr(x), _ptr(gx), *L.params(),
+                                        geo.n_rows, geo.n_inner, geo.n_ch, method, int(code_grad),
+                                        _ptr(noise), seed, offset, _ptr(pdev), _ptr(stats), _ptr(ws), _ptr(tk),
+                                        _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), _stream()),
+              "mhaq_fq_bwd_fused_f32")
+    else:
+        # acc = gradients the same four parameters receive along other paths of the graph
+        # (quantization/gdnsq/_funnel.py): added in the kernel, no accumulation launch
+        check(lib.mhaq_fq_bwd_fused_acc_f32(_ptr(go), _ptr(x), _ptr(gx), *L.params(),
+                                            geo.n_rows, geo.n_inner, geo.n_ch, method, int(code_grad),
+                                            _ptr(noise), seed, offset, _ptr(pdev), _ptr(stats), _ptr(ws), _ptr(tk),
+                                            _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]),
+                                            _ptr(acc[0]), _ptr(acc[1]), _ptr(acc[2]), _ptr(acc[3]), _stream()),
+              "mhaq_fq_bwd_fused_acc_f32")
     return gx, out
 
 
@@ -718,29 +728,41 @@ class _ActFakeQuantFn(torch.autograd.Function):
     backward) autograd would otherwise run per quantizer exist."""
 
     @staticmethod
-    def forward(ctx, x, log_act_s, log_act_q, act_b, method, noise, philox):
+    def forward(ctx, x, log_act_s, log_act_q, act_b, method, noise, philox, funnel=False):
+        ctx.set_materialize_grads(False)
         x = _dense(x, None)
         L = _Launch.act_log(x, log_act_s, log_act_q, act_b)
         y, _, _ = _forward_impl(x, L, True, False, False)
         ctx.save_for_backward(x, log_act_s, log_act_q, act_b)
         ctx.L, ctx.method, ctx.noise, ctx.philox = L, method, noise, philox
+        if funnel:
+            # aliases of the two log parameters as outputs of THIS node: whatever else reads them
+            # (PotentialLoss) sends its gradient back here instead of to the leaves
+            return y, log_act_s.view_as(log_act_s), log_act_q.view_as(log_act_q)
         return y
 
     @staticmethod
-    def backward(ctx, go):
+    def backward(ctx, go, g_las=None, g_laq=None):
         x, log_act_s, log_act_q, act_b = ctx.saved_tensors
         need = ctx.needs_input_grad
-        gx, out = _backward_impl(go, x, ctx.L, ctx.method, False, ctx.noise, need[0], ctx.philox)
+        if go is None:          # only the aliases were used: their gradients pass straight through
+            return (None, g_las if need[1] else None, g_laq if need[2] else None, None, None, None, None, None)
+        acc = None
+        if g_las is not None or g_laq is not None:
+            c = lambda t: None if t is None else t.contiguous()
+            acc = (c(g_las), None, c(g_laq), None)       # kernel outputs: log_act_s, act_b, log_act_q
+        gx, out = _backward_impl(go, x, ctx.L, ctx.method, False, ctx.noise, need[0], ctx.philox, acc=acc)
         return (gx if need[0] else None,
                 out[0].reshape(log_act_s.shape) if need[1] else None,
                 out[2].reshape(log_act_q.shape) if need[2] else None,
-                out[1].reshape(act_b.shape) if need[3] else None, None, None, None)
+                out[1].reshape(act_b.shape) if need[3] else None, None, None, None, None)
 
 
-def act_fake_quant(x, log_act_s, log_act_q, act_b, method="STE", noise=None, philox=None):
-    """Fused NoisyAct: fake_quant(x, s=2^log_act_s, zp=lo=act_b, hi=act_b+2^log_act_q-s)."""
+def act_fake_quant(x, log_act_s, log_act_q, act_b, method="STE", noise=None, philox=None, funnel=False):
+    """Fused NoisyAct: fake_quant(x, s=2^log_act_s, zp=lo=act_b, hi=act_b+2^log_act_q-s).
+    funnel=True -> (y, alias of log_act_s, alias of log_act_q): see quantization/gdnsq/_funnel.py."""
     _require_cuda(x)
-    return _ActFakeQuantFn.apply(x, log_act_s, log_act_q, act_b, _method_id(method), noise, philox)
+    return _ActFakeQuantFn.apply(x, log_act_s, log_act_q, act_b, _method_id(method), noise, philox, funnel)
 
 
 class _WeightLogFakeQuantFn(torch.autograd.Function):
@@ -895,7 +917,7 @@ class _WeightRowMultiFn(torch.autograd.Function):
     backward is one launch too (it runs once the last consumer of any output has run)."""
 
     @staticmethod
-    def forward(ctx, method, noises, philox, n, *tensors):
+    def forward(ctx, method, noises, philox, n, funnel, *tensors):
         from ._lib import WRowFwdDesc
         ctx.set_materialize_grads(False)
         ws = [_dense(w, 0) for w in tensors[:n]]
@@ -918,6 +940,8 @@ class _WeightRowMultiFn(torch.autograd.Function):
         check(lib.mhaq_fq_wrow_multi_fwd_f32(descs, n, _stream()), "mhaq_fq_wrow_multi_fwd_f32")
         ctx.save_for_backward(*ws, *lss, stats)
         ctx.n, ctx.rows, ctx.method, ctx.noises, ctx.philox = n, rows, method, noises, philox
+        if funnel:      # + one alias of every log-scale (quantization/gdnsq/_funnel.py)
+            outs += [ls.view_as(ls) for ls in tensors[n:]]
         return tuple(outs)
 
     @staticmethod
@@ -936,11 +960,12 @@ class _WeightRowMultiFn(torch.autograd.Function):
             g_wq, g_mn, g_mx, g_lr = grads[4 * i: 4 * i + 4]
             g_wq = torch.zeros_like(w) if g_wq is None else _like_layout(g_wq, w)
             g_mn, g_mx, g_lr = c(g_mn), c(g_mx), c(g_lr)
+            g_acc = c(grads[4 * n + i]) if len(grads) > 4 * n else None     # through the log-scale alias
             noise = None if ctx.noises is None else ctx.noises[i]
             if noise is not None:
                 noise = _like_layout(noise, w)
-            gw = torch.empty_like(w) if need[4 + i] else None
-            gls = torch.empty(rows[i], dtype=torch.float32, device=w.device) if need[4 + n + i] else None
+            gw = torch.empty_like(w) if need[5 + i] else None
+            gls = torch.empty(rows[i], dtype=torch.float32, device=w.device) if need[5 + n + i] else None
             r1 = r0 + rows[i]
             d = descs[i]
             d.g_wq, d.w, d.log_scale = g_wq.data_ptr(), w.data_ptr(), ls.data_ptr()
@@ -948,7 +973,8 @@ class _WeightRowMultiFn(torch.autograd.Function):
             d.g_log_range, d.g_row_min, d.g_row_max, d.r = _ptr(g_lr), _ptr(g_mn), _ptr(g_mx), _ptr(noise)
             d.g_w, d.g_log_scale = _ptr(gw), _ptr(gls)
             d.n_rows, d.n_inner = rows[i], w.numel() // rows[i]
-            keep += [g_wq, g_mn, g_mx, g_lr, noise]
+            d.g_log_scale_acc = _ptr(g_acc) if gls is not None else None
+            keep += [g_wq, g_mn, g_mx, g_lr, noise, g_acc]
             gws.append(gw)
             glss.append(None if gls is None else gls.reshape(ls.shape))
             r0 = r1
@@ -966,12 +992,13 @@ class _WeightRowMultiFn(torch.autograd.Function):
         check(lib.mhaq_fq_wrow_multi_bwd_f32(descs, n, ctx.method, seed, offset, _ptr(pdev), _ptr(ae_stats),
                                              total_rows, _stream()),
               "mhaq_fq_wrow_multi_bwd_f32")
-        return (None, None, None, None, *gws, *glss)
+        return (None, None, None, None, None, *gws, *glss)
 
 
-def weight_fake_quant_rows_multi(weights, log_scales, method="STE", noises=None, philox=None):
+def weight_fake_quant_rows_multi(weights, log_scales, method="STE", noises=None, philox=None, funnel=False):
     """[(wq, row_min, row_max, log_range), ...] for a list of per-channel weights with short rows
-    (each must satisfy `weight_rows_fusable`), one launch each way for the whole list."""
+    (each must satisfy `weight_rows_fusable`), one launch each way for the whole list.
+    funnel=True appends an alias of the tensor's log-scale to every tuple (quantization/gdnsq/_funnel.py)."""
     n = len(weights)
     if n == 0:
         return []
@@ -983,7 +1010,9 @@ def weight_fake_quant_rows_multi(weights, log_scales, method="STE", noises=None,
                                f"and rows of at most {WROW_MAX_INNER} elements")
     if mid == METHOD_IDS["LSQ"]:
         noises = None
-    out = _WeightRowMultiFn.apply(mid, noises, philox, n, *weights, *log_scales)
+    out = _WeightRowMultiFn.apply(mid, noises, philox, n, bool(funnel), *weights, *log_scales)
+    if funnel:
+        return [tuple(out[4 * i: 4 * i + 4]) + (out[4 * n + i],) for i in range(n)]
     return [tuple(out[4 * i: 4 * i + 4]) for i in range(n)]
 
 

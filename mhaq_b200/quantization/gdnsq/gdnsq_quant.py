@@ -29,6 +29,7 @@ from torch import nn
 from ...aux.qutils import attrsetter, is_biased
 from ...aux.types import QScheme, scheme_id
 from ..abc.abc_quant import BaseQuant
+from . import _funnel
 from .distill_losses import get_distillation_loss
 from .gdnsq_loss import PotentialLoss, PotentialLossNoPred
 from .gdnsq_utils import QNMethod
@@ -158,10 +159,11 @@ class GDNSQQuant(BaseQuant):
         self = train_step.__self__
 
         def wrapper(batch, batch_idx):
-            prequantize_weights(self.model)      # every conv weight in one launch (layers/_multi.py)
-            outputs = (train_step(batch, batch_idx),
-                       *ModelHelper.get_model_values(self.model, self.qscheme))
-            loss = self.wrapped_criterion(outputs)
+            with _funnel.step():                     # one gradient per quantizer parameter (_funnel.py)
+                prequantize_weights(self.model)      # every conv weight in one launch (layers/_multi.py)
+                outputs = (train_step(batch, batch_idx),
+                           *ModelHelper.get_model_values(self.model, self.qscheme))
+                loss = self.wrapped_criterion(outputs)
             GDNSQQuant._log_train(self, loss)
             return loss
 
@@ -169,8 +171,9 @@ class GDNSQQuant(BaseQuant):
 
     @staticmethod
     def noisy_step(self, x):
-        prequantize_weights(self.model)          # every conv weight in one launch (layers/_multi.py)
-        return (self.forward(x), *ModelHelper.get_model_values(self.model, self.qscheme))
+        with _funnel.step():                         # one gradient per quantizer parameter (_funnel.py)
+            prequantize_weights(self.model)          # every conv weight in one launch (layers/_multi.py)
+            return (self.forward(x), *ModelHelper.get_model_values(self.model, self.qscheme))
 
     @staticmethod
     def distillation_noisy_training_step(self, batch, batch_idx):

@@ -19,6 +19,7 @@ import torch
 import torch.distributed as dist
 
 from .... import ops
+from .. import _funnel
 from .gdnsq_conv2d import NoisyConv2d
 
 
@@ -49,9 +50,11 @@ def prequantize_weights(model: torch.nn.Module) -> int:
         per = -(-len(items) // n_groups)
         for g0 in range(0, len(items), per):
             part = items[g0:g0 + per]
+            funnel = _funnel.active()
             res = ops.weight_fake_quant_rows_multi([m.weight for m, _ in part],
-                                                   [m.log_wght_s for m, _ in part], method=method)
-            for (m, key), (wq, mn, mx, lr) in zip(part, res):
-                m.adopt_quantized(key, wq, mn, mx, lr)
+                                                   [m.log_wght_s for m, _ in part], method=method,
+                                                   funnel=funnel)
+            for (m, key), out in zip(part, res):
+                m.adopt_quantized(key, *out)
         served += len(items)
     return served

@@ -11,6 +11,7 @@ import torch
 from torch import nn, inf
 
 from .... import ops
+from .. import _funnel
 from ..gdnsq import Quantizer
 from ..gdnsq_utils import QNMethod
 
@@ -50,6 +51,14 @@ class NoisyAct(nn.Module):
             # fused: the kernels read log_act_s / log_act_q / act_b themselves and return the
             # log-domain gradients; Q.scale & co. are materialised only if somebody reads them
             self.Q.defer(self._operands)
+            if _funnel.active() and torch.is_grad_enabled() and self.log_act_s.requires_grad:
+                # one gradient per parameter: PotentialLoss reads these aliases (via ModelHelper)
+                # and its gradient comes back into this node's backward kernel (_funnel.py)
+                y, las, laq = ops.act_fake_quant(x, self.log_act_s, self.log_act_q, self.act_b,
+                                                 method=self.Q._method(), funnel=True)
+                self._funnel_act = (las, laq)
+                _funnel.hold(self)
+                return y
             return ops.act_fake_quant(x, self.log_act_s, self.log_act_q, self.act_b,
                                       method=self.Q._method())
         self.Q.scale, self.Q.zero_point, self.Q.min_val, self.Q.max_val = self._operands()

@@ -105,9 +105,14 @@ class NoisyConv2d(nn.Conv2d):
         return self._wq_cache.lookup((self.weight, self.log_wght_s, self.bias),
                                      torch.is_grad_enabled(), self.training)
 
-    def adopt_quantized(self, key, wq, mn, mx, lr):
+    def adopt_quantized(self, key, wq, mn, mx, lr, ls_alias=None):
         """Install (weight_q, row_min, row_max, log_range) computed by the multi-tensor launch as
-        this step's cache entry, exactly what `_quantize` would have stored."""
+        this step's cache entry, exactly what `_quantize` would have stored.  `ls_alias`: this
+        step's alias of log_wght_s for ModelHelper (gradient funnel, ../_funnel.py)."""
+        if ls_alias is not None:
+            from .. import _funnel
+            self._funnel_ls = ls_alias
+            _funnel.hold(self)
         pshape = (self.weight.shape[0],) + (1,) * (self.weight.dim() - 1)
         log_s, q = self.log_wght_s, self.Q
         q.defer(lambda: (torch.exp2(log_s).reshape(pshape), mn.view(pshape), q._min_val, q._max_val))

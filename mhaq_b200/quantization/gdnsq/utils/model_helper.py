@@ -21,7 +21,10 @@ class ModelHelper:
                     continue
                 if is_per_channel(qscheme):
                     dims = tuple(range(1, m.weight.dim()))
-                    log_wght_s.append(m.log_wght_s.ravel())
+                    # (this step's alias of log_wght_s when the gradient funnel is active: the
+                    # loss's gradient then returns through the weight kernel, ../_funnel.py)
+                    ls = m.__dict__.pop("_funnel_ls", None)
+                    log_wght_s.append((m.log_wght_s if ls is None else ls).ravel())
                     # the layer already reduced the weight rows in this step's forward: the
                     # fused row kernels hand back log2(max - min + 2^log_wght_s) itself, the
                     # streaming path its differentiable (min, max) — either way no further
@@ -40,8 +43,9 @@ class ModelHelper:
                 log_w_n_b.append(torch.log2(mx - mn + torch.exp2(m.log_wght_s.ravel())))
             elif isinstance(m, NoisyAct):
                 if m.log_act_s.requires_grad:
-                    log_act_q.append(m.log_act_q)
-                    log_act_s.append(m.log_act_s)
+                    las, laq = m.__dict__.pop("_funnel_act", None) or (m.log_act_s, m.log_act_q)
+                    log_act_q.append(laq)
+                    log_act_s.append(las)
         if is_per_tensor(qscheme):
             return (torch.stack(log_act_s).ravel(), torch.stack(log_act_q).ravel(),
                     torch.stack(log_wght_s).ravel(), torch.stack(log_w_n_b).ravel())

@@ -27,7 +27,7 @@ def test_header_symbols_all_exported():
 
 def test_abi_version_and_info():
     from mhaq_b200 import _lib
-    assert _lib.lib.mhaq_fq_abi_version() == 6
+    assert _lib.lib.mhaq_fq_abi_version() == 7
     assert b"sm_100a" in _lib.lib.mhaq_fq_build_info()
 
 

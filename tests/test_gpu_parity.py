@@ -899,6 +899,65 @@ def test_multi_tensor_launch_serves_the_layers_and_unused_outputs(fq):
         H.assert_close_rel(g1[n], g2[n], 1e-5, n, abs_floor=1e-6 * float(g2[n].abs().max()) + 1e-12)
 
 
+@pytest.mark.parametrize("method,distill", [("STE", True), ("LSQ", False), ("AEWGS", True)])
+def test_gradient_funnel_gives_the_same_gradients_with_fewer_launches(fq, method, distill):
+    """quantization/gdnsq/_funnel.py: PotentialLoss's gradients w.r.t. log_act_s / log_act_q /
+    log_wght_s return through the quantizer nodes and are added inside their backward kernels.
+    Same loss, bitwise the same gradient for EVERY parameter (an fp32 add commutes; same Philox
+    streams in both runs), and 2 launches per activation quantizer + 1 per conv weight fewer."""
+    import contextlib
+    from torch.profiler import profile, ProfilerActivity
+    from mhaq_b200 import harness
+    import mhaq_b200.quantization.gdnsq._funnel as FN
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_act import NoisyAct
+    from mhaq_b200.quantization.gdnsq.layers.gdnsq_conv2d import NoisyConv2d
+    torch.manual_seed(0)
+    x = torch.randn(32, 3, 32, 32, device="cuda")
+    t = torch.randint(0, 10, (32,), device="cuda")
+    q = harness.build_qat("resnet20", "cuda", qnmethod=method, act_bit=4, weight_bit=4, distillation=distill,
+                          num_classes=10, calib_batch=x)
+    q.train(); q.wrapped_criterion.train()
+    if getattr(q, "tmodel", None) is not None:
+        q.tmodel.eval()
+    n_act = sum(isinstance(m, NoisyAct) for m in q.model.modules())
+    n_conv = sum(isinstance(m, NoisyConv2d) for m in q.model.modules())
+    saved_flags = (torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = False, True, False
+    real_step = FN.step
+    runs = []
+    try:
+        for funnel in (True, False):
+            FN.step = real_step if funnel else contextlib.nullcontext
+
+            def one_step():
+                fq.ops.set_device_philox_state(torch.tensor([5, 0], dtype=torch.int64, device="cuda"))
+                fq.ops.reset_philox_call_counter()
+                q.wrapped_criterion.loss_sum, q.wrapped_criterion.cnt = 0.0, 1
+                loss = q.training_step((x, t), 0)
+                loss.backward()
+                return loss
+            one_step(); q.zero_grad(set_to_none=True)                  # warm-up (cuDNN plans, arenas)
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                loss = one_step()
+                torch.cuda.synchronize()
+            launches = sum(ev.count for ev in prof.key_averages()
+                           if (getattr(ev, "device_time_total", 0.0) or 0.0) > 0)
+            runs.append((loss.detach().clone(), {n: p.grad.clone() for n, p in q.named_parameters() if p.grad is not None},
+                         launches))
+            q.zero_grad(set_to_none=True)
+    finally:
+        FN.step = real_step
+        fq.ops.set_device_philox_state(None)
+        torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = saved_flags
+    (l1, g1, k1), (l2, g2, k2) = runs
+    assert torch.equal(l1, l2)
+    assert set(g1) == set(g2)
+    for n in g1:
+        assert torch.equal(g1[n], g2[n]), n
+    assert not FN._holders and not any("_funnel_act" in m.__dict__ or "_funnel_ls" in m.__dict__ for m in q.model.modules())
+    assert k2 - k1 >= 2 * n_act + n_conv - 2, (k1, k2, n_act, n_conv)
+
+
 # ---------------------------------------------------------------------------
 # fused PotentialLoss arithmetic (mhaq_fq_potential_loss_*)
 # ---------------------------------------------------------------------------
