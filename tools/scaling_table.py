@@ -86,7 +86,7 @@ def main():
             "flags the step is 37-39 ms: SyncBatchNorm's all-gathers around every one of the 20 BatchNorm layers (forward and "
             "backward), the per-step graph traversal of `find_unused_parameters=True`, the buffer broadcast, and eager "
             "launches instead of one graph launch.",
-            "* **ResNet-20 AEWGS (configs[2])**: a 5.8 ms step, so latency-bound: DDP costs 0.35-0.6 ms whatever N is.  "
+            "* **ResNet-20 AEWGS (configs[2])**: a 6 ms step, so latency-bound: DDP costs 0.1-0.2 ms whatever N is.  "
             "The path's one collective — the packed statistics all-reduce, ONE per step for all 18 conv weights — sits in "
             "the middle of the weight backward (the apply kernel needs the averaged statistics), so one NCCL latency plus the "
             "skew between ranks at that point is exposed; the gradient all-reduce (0.27 M parameters, one bucket) follows at "
